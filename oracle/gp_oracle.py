@@ -1,0 +1,456 @@
+"""CPU oracle for the GP hot path of bbbales2/gp  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product path (gp_b200/) never does: it fails loudly when the CUDA
+library is missing.
+
+PARITY STATUS: "parity unpinned" for the Stan-Math rows (a1-a8): the reference stores no golden
+output for this path and its arithmetic lives in Stan Math / Eigen / R, none of which is vendored or
+installable here (no R, Rcpp, StanHeaders, Eigen in this image).  Those rows restate the published
+semantics of Stan Math 2.15-2.17 (the era the reference was written against; no version is pinned
+in the reference) at the reference's own call sites.  Rows a9/a10 (derivative kernels, noise-added
+solve) ARE pinned: tests/golden/gp_derivs_golden.npz holds the outputs of the reference's own
+gp_derivs.py executed in the build container (tests/golden/make_golden.py).
+
+Every function cites the reference file:line (relative to /root/reference) that it restates.
+All arithmetic is IEEE float64 through NumPy/SciPy (LAPACK potrf/trtrs via OpenBLAS).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+LOG_TWO_PI = math.log(2.0 * math.pi)
+
+
+# --------------------------------------------------------------------------------------------------
+# a4  cov_exp_quad  (models/fit_hyperparameters.stan:19, exact_gp.stan:17, fit_full_gp.stan:18,
+#     heteroscedastic.stan:23, westbrook_exact.stan:17, interpolated_gp.stan:10,16)
+# Stan Math semantics: K[i,i] = alpha^2 exactly; K[i,j] = alpha^2 * exp(-0.5 * (x_i-x_j)^2 / rho^2)
+# for the lower triangle, mirrored into the upper.
+# --------------------------------------------------------------------------------------------------
+def cov_exp_quad(x, alpha, rho):
+    x = np.asarray(x, dtype=np.float64)
+    d = x[:, None] - x[None, :]
+    K = (alpha * alpha) * np.exp(-0.5 * (d * d) / (rho * rho))
+    K = np.tril(K) + np.tril(K, -1).T
+    K[np.diag_indices_from(K)] = alpha * alpha
+    return K
+
+
+# a5  diagonal add (fit_hyperparameters.stan:21-24 sigma^2; exact_gp.stan:20-22 1e-10; ...)
+def add_diag(K, c):
+    K = np.array(K, dtype=np.float64, copy=True)
+    K[np.diag_indices_from(K)] += c
+    return K
+
+
+class NotPositiveDefinite(ValueError):
+    """Stan Math cholesky_decompose throws std::domain_error when the matrix is not symmetric
+    (abs tol 1e-8) or not positive definite; `info` is the LAPACK-style 1-based index of the first
+    non-positive pivot (0 when the failure is a symmetry failure)."""
+
+    def __init__(self, msg, info=0):
+        super().__init__(msg)
+        self.info = info
+
+
+# a6  cholesky_decompose (fit_hyperparameters.stan:25, exact_gp.stan:23, covariance.cpp:29, ...)
+def cholesky_decompose(K):
+    K = np.asarray(K, dtype=np.float64)
+    if K.ndim != 2 or K.shape[0] != K.shape[1]:
+        raise NotPositiveDefinite("cholesky_decompose: matrix is not square")
+    if K.size and np.max(np.abs(K - K.T)) > 1e-8:
+        raise NotPositiveDefinite("cholesky_decompose: matrix is not symmetric")
+    L, info = sla.lapack.dpotrf(K, lower=1, clean=1)
+    if info != 0:
+        raise NotPositiveDefinite("cholesky_decompose: matrix is not positive definite", int(info))
+    return L
+
+
+def potrf_info(K):
+    """LAPACK-convention info of the factorisation (0 ok, k>0 first non-positive pivot)."""
+    _, info = sla.lapack.dpotrf(np.asarray(K, dtype=np.float64), lower=1, clean=1)
+    return int(info)
+
+
+# mdivide_left_tri_low (inside multi_normal_cholesky; fit_hyperparameters.stan:31)
+def mdivide_left_tri_low(L, b):
+    return sla.solve_triangular(L, b, lower=True, check_finite=False)
+
+
+def mdivide_right_tri_low_T(L, b):
+    """solve L^T x = b."""
+    return sla.solve_triangular(L, b, lower=True, trans="T", check_finite=False)
+
+
+# a7  multi_normal_cholesky_lpdf (fit_hyperparameters.stan:31; heteroscedastic_centered.stan:33-34)
+# lp = [-0.5 N log(2 pi)] - sum(log L_ii) - 0.5 ||L^-1 (y - mu)||^2 ; the bracket is dropped under `~`.
+def multi_normal_cholesky_lpdf(y, mu, L, drop_constants=False):
+    y = np.asarray(y, dtype=np.float64)
+    mu = np.broadcast_to(np.asarray(mu, dtype=np.float64), y.shape)
+    z = mdivide_left_tri_low(L, y - mu)
+    lp = -np.sum(np.log(np.diag(L))) - 0.5 * float(z @ z)
+    if not drop_constants:
+        lp -= 0.5 * y.shape[0] * LOG_TWO_PI
+    return float(lp)
+
+
+# a8  non-centred mat-vec f = L z (exact_gp.stan:25, fit_full_gp.stan:26, heteroscedastic.stan:31-32)
+def trmv_lower(L, z):
+    return np.tril(L) @ np.asarray(z, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------------
+# CS-A: the model block of models/fit_hyperparameters.stan:18-31 as a pure function of
+# theta = (alpha, rho, sigma):  K = cov_exp_quad + (sigma^2 + jitter) I ; LML = MVN(y | 0, K).
+# --------------------------------------------------------------------------------------------------
+def gram_se(x, alpha, rho, diag_add):
+    return add_diag(cov_exp_quad(x, alpha, rho), diag_add)
+
+
+def lml(x, y, alpha, rho, sigma, jitter=0.0, drop_constants=False):
+    K = gram_se(x, alpha, rho, sigma * sigma + jitter)
+    L = cholesky_decompose(K)
+    return multi_normal_cholesky_lpdf(y, 0.0, L, drop_constants)
+
+
+def lml_grad(x, y, alpha, rho, sigma, jitter=0.0):
+    """LML and its gradient w.r.t. (alpha, rho, sigma) -- what Stan's reverse sweep through
+    multi_normal_cholesky -> cholesky_decompose -> cov_exp_quad returns:
+      dLML/dtheta_p = 0.5 tr((a a^T - K^-1) dK/dtheta_p), a = K^-1 y,
+      dK/dalpha = 2 K_se / alpha, dK/drho = K_se * d^2 / rho^3, dK/dsigma = 2 sigma I."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = x.shape[0]
+    Kse = cov_exp_quad(x, alpha, rho)
+    K = add_diag(Kse, sigma * sigma + jitter)
+    L = cholesky_decompose(K)
+    z = mdivide_left_tri_low(L, y)
+    a = mdivide_right_tri_low_T(L, z)
+    val = -0.5 * n * LOG_TWO_PI - np.sum(np.log(np.diag(L))) - 0.5 * float(z @ z)
+    Linv = sla.solve_triangular(L, np.eye(n), lower=True, check_finite=False)
+    Kinv = Linv.T @ Linv
+    M = np.outer(a, a) - Kinv
+    d = x[:, None] - x[None, :]
+    g_alpha = 0.5 * np.sum(M * (2.0 * Kse / alpha))
+    g_rho = 0.5 * np.sum(M * (Kse * (d * d) / rho ** 3))
+    g_sigma = 0.5 * np.trace(M) * 2.0 * sigma
+    return float(val), np.array([g_alpha, g_rho, g_sigma])
+
+
+def lp_fit_hyperparameters(x, y, log_rho, log_alpha, log_sigma):
+    """`lp__`-compatible value of models/fit_hyperparameters.stan on the unconstrained scale:
+    likelihood with dropped constant (`~`, :31) + gamma(4,4) / normal(0,1) priors with their
+    dropped constants (:27-29) + log-Jacobians of the <lower=0> transforms (:13-15)."""
+    rho, alpha, sigma = math.exp(log_rho), math.exp(log_alpha), math.exp(log_sigma)
+    lp = lml(x, y, alpha, rho, sigma, drop_constants=True)
+    lp += 3.0 * math.log(rho) - 4.0 * rho          # gamma(4,4) kernel
+    lp += -0.5 * alpha * alpha - 0.5 * sigma * sigma  # normal(0,1) kernels
+    lp += log_rho + log_alpha + log_sigma           # Jacobians
+    return lp
+
+
+# --------------------------------------------------------------------------------------------------
+# a1-a3  rbf_cov_chol (covariance.cpp:9-47): unit-amplitude SE Gram over the FULL square
+# exp(-(xi-xj)^2/(2 l^2)) (:17-21), + 1e-10 on the diagonal (:23-25), Cholesky carried in
+# forward-mode duals seeded on l (:13,29); returns L (value) and dLdl (tangent), upper = 0.
+# Closed form of the tangent: Ldot = L Phi(L^-1 Kdot L^-T),
+# Phi = tril with halved diagonal, Kdot = K_se * d^2 / l^3.
+# --------------------------------------------------------------------------------------------------
+RBF_JITTER = 1e-10
+
+
+def rbf_gram_and_tangent(x1, l, jitter=RBF_JITTER):
+    x1 = np.asarray(x1, dtype=np.float64)
+    d = x1[:, None] - x1[None, :]
+    d2 = d * d
+    S = np.exp(-d2 / (2.0 * l * l))
+    Sdot = S * d2 / (l ** 3)
+    S = add_diag(S, jitter)
+    return S, Sdot
+
+
+def phi_lower(A):
+    P = np.tril(A)
+    P[np.diag_indices_from(P)] *= 0.5
+    return P
+
+
+def rbf_cov_chol(x1, l, jitter=RBF_JITTER):
+    S, Sdot = rbf_gram_and_tangent(x1, l, jitter)
+    L = cholesky_decompose(S)
+    T = sla.solve_triangular(L, Sdot, lower=True, check_finite=False)
+    A = sla.solve_triangular(L, T.T, lower=True, check_finite=False).T
+    dLdl = L @ phi_lower(A)
+    return L, np.tril(dLdl)
+
+
+def rbf_cov_chol_dual(x1, l, jitter=RBF_JITTER):
+    """Literal restatement of covariance.cpp:13-39: an unblocked LLT executed on (value, tangent)
+    pairs, i.e. what Eigen's LLT does when instantiated on stan::math::fvar<double>.  O(N^3)
+    Python-level work: small N only.  Used to pin the closed form above."""
+    S, Sdot = rbf_gram_and_tangent(x1, l, jitter)
+    n = S.shape[0]
+    Lv = np.zeros((n, n))
+    Lt = np.zeros((n, n))
+    for j in range(n):
+        sv = S[j, j] - Lv[j, :j] @ Lv[j, :j]
+        st = Sdot[j, j] - 2.0 * (Lv[j, :j] @ Lt[j, :j])
+        if not sv > 0.0:
+            raise NotPositiveDefinite("rbf_cov_chol: not positive definite", j + 1)
+        dv = math.sqrt(sv)
+        dt = 0.5 * st / dv
+        Lv[j, j], Lt[j, j] = dv, dt
+        if j + 1 < n:
+            cv = S[j + 1:, j] - Lv[j + 1:, :j] @ Lv[j, :j]
+            ct = Sdot[j + 1:, j] - Lv[j + 1:, :j] @ Lt[j, :j] - Lt[j + 1:, :j] @ Lv[j, :j]
+            Lv[j + 1:, j] = cv / dv
+            Lt[j + 1:, j] = (ct - Lv[j + 1:, j] * dt) / dv
+    return Lv, Lt
+
+
+# --------------------------------------------------------------------------------------------------
+# a9  derivative kernels, API #2 (derivative_kernels.R:39-73): unit amplitude, scalar l,
+# element-wise in (tj, tk).  Q = value, R = first derivative, T = second derivative.
+# --------------------------------------------------------------------------------------------------
+def _e(tj, tk, l):
+    tj = np.asarray(tj, dtype=np.float64)
+    tk = np.asarray(tk, dtype=np.float64)
+    d = tj - tk
+    return np.exp(-(d ** 2 / (2.0 * l ** 2))), d
+
+
+def dk_QQ(tj, tk, l):  # derivative_kernels.R:39-41
+    e, _ = _e(tj, tk, l)
+    return e
+
+
+def dk_QR(tj, tk, l):  # :43-45
+    e, d = _e(tj, tk, l)
+    return (e * d) / l ** 2
+
+
+def dk_RQ(tj, tk, l):  # :47-49
+    return dk_QR(tk, tj, l)
+
+
+def dk_RR(tj, tk, l):  # :51-53
+    e, d = _e(tj, tk, l)
+    return e / l ** 2 - (e * d ** 2) / l ** 4
+
+
+def dk_QT(tj, tk, l):  # :55-57
+    e, d = _e(tj, tk, l)
+    return -(e / l ** 2) + (e * d ** 2) / l ** 4
+
+
+def dk_TQ(tj, tk, l):  # :59-61
+    return dk_QT(tk, tj, l)
+
+
+def dk_RT(tj, tk, l):  # :63-65
+    e, d = _e(tj, tk, l)
+    return (3.0 * e * d) / l ** 4 - (e * d ** 3) / l ** 6
+
+
+def dk_TR(tj, tk, l):  # :67-69
+    return dk_RT(tk, tj, l)
+
+
+def dk_TT(tj, tk, l):  # :71-73
+    e, d = _e(tj, tk, l)
+    return (3.0 * e) / l ** 4 - (6.0 * e * d ** 2) / l ** 6 + (e * d ** 4) / l ** 8
+
+
+DERIV_KERNELS = {"QQ": dk_QQ, "QR": dk_QR, "RQ": dk_RQ, "RR": dk_RR, "QT": dk_QT, "TQ": dk_TQ,
+                 "RT": dk_RT, "TR": dk_TR, "TT": dk_TT}
+
+
+def outer_kernel(name, tj, tk, l):
+    """R's outer(tj, tk, FUN = function(a, b) kern(a, b, l)) (pendulum_fit.R:238-240)."""
+    tj = np.asarray(tj, dtype=np.float64)
+    tk = np.asarray(tk, dtype=np.float64)
+    return DERIV_KERNELS[name](tj[:, None], tk[None, :], l)
+
+
+# --------------------------------------------------------------------------------------------------
+# a9  R kernel API #1 (R/kernels.R:19-32), phi = (alpha, rho); outer() semantics.
+# RR reproduces the operator-precedence quirk of R/kernels.R:31 (phi1^2 multiplies only the first
+# term) unless quirk=False.
+# --------------------------------------------------------------------------------------------------
+def rk_QQ(x, y, phi):  # R/kernels.R:22-24
+    e, _ = _e(np.asarray(x, float)[:, None], np.asarray(y, float)[None, :], phi[1])
+    return phi[0] ** 2 * e
+
+
+def rk_QR(x, y, phi):  # R/kernels.R:26-28
+    e, d = _e(np.asarray(x, float)[:, None], np.asarray(y, float)[None, :], phi[1])
+    return phi[0] ** 2 * (e * d) / phi[1] ** 2
+
+
+def rk_RR(x, y, phi, quirk=True):  # R/kernels.R:30-32
+    e, d = _e(np.asarray(x, float)[:, None], np.asarray(y, float)[None, :], phi[1])
+    second = (e * d ** 2) / phi[1] ** 4
+    if not quirk:
+        second = phi[0] ** 2 * second
+    return phi[0] ** 2 * e / phi[1] ** 2 - second
+
+
+def rk_QQard(X, Y, phi):  # R/kernels.R:19 ; phi = (alpha, rho[D] or scalar)
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    Y = np.atleast_2d(np.asarray(Y, dtype=np.float64))
+    rho = np.broadcast_to(np.asarray(phi[1], dtype=np.float64), (X.shape[1],))
+    diff = (X[:, None, :] - Y[None, :, :]) / rho[None, None, :]
+    return phi[0] ** 2 * np.exp(-0.5 * np.sum(diff ** 2, axis=2))
+
+
+# --------------------------------------------------------------------------------------------------
+# C2 joint covariance of (y, y', y'') on one grid: blocks {QQ,QR,QT; RQ,RR,RT; TQ,TR,TT} * alpha^2
+# + diag(noise_y^2, noise_yp^2, noise_ypp^2) + jitter I (design_notes.Rmd:6-46).
+# --------------------------------------------------------------------------------------------------
+_JOINT = [["QQ", "QR", "QT"], ["RQ", "RR", "RT"], ["TQ", "TR", "TT"]]
+
+
+def gram_deriv(t, alpha, rho, noise, jitter, nblocks=3):
+    t = np.asarray(t, dtype=np.float64)
+    n = t.shape[0]
+    K = np.empty((nblocks * n, nblocks * n))
+    for bi in range(nblocks):
+        for bj in range(nblocks):
+            K[bi * n:(bi + 1) * n, bj * n:(bj + 1) * n] = alpha ** 2 * outer_kernel(_JOINT[bi][bj], t, t, rho)
+    for bi in range(nblocks):
+        idx = np.arange(bi * n, (bi + 1) * n)
+        K[idx, idx] += noise[bi] ** 2 + jitter
+    return K
+
+
+# --------------------------------------------------------------------------------------------------
+# a10 conditioning
+# --------------------------------------------------------------------------------------------------
+def condMVN(mean, sigma, dependent_ind, given_ind=None, X_given=None):
+    """condMVNorm::condMVN as called at ode_gp_library.R:17,32 (0-based index arrays here):
+    condMean = m_d + C D^-1 (X - m_g), condVar = B - C D^-1 C^T with B, C, D the
+    dependent/cross/given blocks of sigma."""
+    mean = np.asarray(mean, dtype=np.float64)
+    sigma = np.asarray(sigma, dtype=np.float64)
+    dep = np.asarray(dependent_ind)
+    if given_ind is None or len(given_ind) == 0:
+        return mean[dep].copy(), sigma[np.ix_(dep, dep)].copy()
+    giv = np.asarray(given_ind)
+    B = sigma[np.ix_(dep, dep)]
+    C = sigma[np.ix_(dep, giv)]
+    D = sigma[np.ix_(giv, giv)]
+    CDinv = np.linalg.solve(D, C.T).T
+    cmean = mean[dep] + CDinv @ (np.asarray(X_given, dtype=np.float64) - mean[giv])
+    cvar = B - CDinv @ C.T
+    return cmean, cvar
+
+
+def p_dotXn(tn, Xn, phi_n, sigma_n, quirk=True):
+    """R/ode_gp_library.R:23-33 with UU/UD/DD = QQ/QR/RR of R/kernels.R."""
+    tn = np.asarray(tn, dtype=np.float64)
+    n = tn.shape[0]
+    UU, UD, DD = rk_QQ(tn, tn, phi_n), rk_QR(tn, tn, phi_n), rk_RR(tn, tn, phi_n, quirk)
+    K = np.block([[UU + sigma_n ** 2 * np.eye(n), UD], [UD.T, DD]]) + 1e-6 * np.eye(2 * n)
+    return condMVN(np.zeros(2 * n), K, np.arange(n, 2 * n), np.arange(n), Xn)
+
+
+def p_Xn(tn, Xn, phi_n, sigma_n):
+    """R/ode_gp_library.R:3-18."""
+    tn = np.asarray(tn, dtype=np.float64)
+    n = tn.shape[0]
+    UU = rk_QQ(tn, tn, phi_n)
+    K = np.block([[UU + sigma_n ** 2 * np.eye(n), UU.T], [UU.T, UU]]) + 1e-6 * np.eye(2 * n)
+    return condMVN(np.zeros(2 * n), K, np.arange(n, 2 * n), np.arange(n), Xn)
+
+
+def p_dotXn_solve(tn, Xn, phi_n, sigma_n, quirk=True):
+    """R/ode_gp.R:19-32: mn = RQ (QQ + s^2 I)^-1 Xn ; Kn = RR - RQ (QQ + s^2 I)^-1 QR."""
+    tn = np.asarray(tn, dtype=np.float64)
+    n = tn.shape[0]
+    QQ, QR, RR = rk_QQ(tn, tn, phi_n), rk_QR(tn, tn, phi_n), rk_RR(tn, tn, phi_n, quirk)
+    RQ = QR.T
+    A = QQ + sigma_n ** 2 * np.eye(n)
+    return RQ @ np.linalg.solve(A, np.asarray(Xn, float)), RR - RQ @ np.linalg.solve(A, QR)
+
+
+def gp_condition(K, KsK, KsKs, y, noise_var, jitter):
+    """The shared shape of pendulum_fit.R:242-251 / gp_derivs.py:97-113:
+    mu = KsK (K + s^2 I)^-1 y ; cov = KsKs - KsK (K + s^2 I)^-1 KsK^T + jitter I."""
+    Kt = add_diag(K, noise_var)
+    mu = KsK @ np.linalg.solve(Kt, np.asarray(y, float))
+    cov = KsKs - KsK @ np.linalg.solve(Kt, KsK.T) + jitter * np.eye(KsKs.shape[0])
+    return mu, cov
+
+
+def sample_derivs_moments(params, ynoise, ti):
+    """pendulum_fit.R:227-251 up to (not including) the mvrnorm draw: params = (l, a, sy)."""
+    l, a, sy = params
+    K = a ** 2 * outer_kernel("QQ", ti, ti, l)
+    KsK = a ** 2 * outer_kernel("RQ", ti, ti, l)
+    KsKs = a ** 2 * outer_kernel("RR", ti, ti, l)
+    return gp_condition(K, KsK, KsKs, ynoise, sy ** 2, 1e-8)
+
+
+# --------------------------------------------------------------------------------------------------
+# f-1 cubic-Hermite interpolation of tabulated Cholesky factors (covariance.cpp:49-96;
+# models/cubic_interpolated_gp.hpp:46-72; formula check cubic_spline_test.R:13-18)
+# --------------------------------------------------------------------------------------------------
+def _bracket(l, lp):
+    lidx = 0
+    while lidx < len(lp) - 1:       # covariance.cpp:57-61
+        if lp[lidx + 1] >= l:
+            break
+        lidx += 1
+    lidx = min(lidx, len(lp) - 2)
+    return lidx
+
+
+def approx_L(l, lp, Ls, dLdls):
+    lidx = _bracket(l, lp)
+    x1, x2 = lp[lidx], lp[lidx + 1]
+    t = (l - x1) / (x2 - x1)
+    y1, y2 = np.tril(Ls[lidx]), np.tril(Ls[lidx + 1])
+    k1, k2 = np.tril(dLdls[lidx]), np.tril(dLdls[lidx + 1])
+    a = k1 * (x2 - x1) - (y2 - y1)
+    b = -k2 * (x2 - x1) + (y2 - y1)
+    return (1 - t) * y1 + t * y2 + t * (1 - t) * (a * (1 - t) + b * t)
+
+
+def approx_Lz(l, lp, Ls, dLdls, z):
+    """cubic_interpolated_gp.hpp:46-72: returns (v z, dv/dl z): value and the partial that the
+    hand-built precomp_v_vari carries."""
+    lidx = _bracket(l, lp)
+    x1, x2 = lp[lidx], lp[lidx + 1]
+    t = (l - x1) / (x2 - x1)
+    dtdl = 1.0 / (x2 - x1)
+    y1, y2 = np.asarray(Ls[lidx]), np.asarray(Ls[lidx + 1])
+    k1, k2 = np.asarray(dLdls[lidx]), np.asarray(dLdls[lidx + 1])
+    a = k1 * (x2 - x1) - (y2 - y1)
+    b = -k2 * (x2 - x1) + (y2 - y1)
+    v = (1 - t) * y1 + t * y2 + t * (1 - t) * (a * (1 - t) + b * t)
+    dvdl = (b * (2 - 3 * t) * t + a * (1 + t * (-4 + 3 * t)) - y1 + y2) * dtdl
+    z = np.asarray(z, dtype=np.float64)
+    return v @ z, dvdl @ z
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic workloads of SURVEY 8d (shared by tests and bench so both see the same inputs)
+# --------------------------------------------------------------------------------------------------
+def synth_xy(n, seed, exact_gp_draw=None):
+    rng = np.random.default_rng(seed)
+    x = np.sort(rng.uniform(0.0, 0.05 * n, size=n))
+    f = np.sin(x) + 0.5 * np.sin(3.1 * x)
+    y = f + 0.3 * rng.standard_normal(n)
+    return x, y
+
+
+def synth_theta(B, seed):
+    rng = np.random.default_rng(seed)
+    alpha = np.abs(rng.standard_normal(B)) + 0.1
+    rho = rng.gamma(4.0, 1.0 / 4.0, size=B)
+    sigma = rng.uniform(0.1, 0.5, size=B)
+    return np.stack([alpha, rho, sigma], axis=1)
