@@ -1,0 +1,100 @@
+// Shared definitions for libgpb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace gpb {
+
+constexpr int TILE = 128;  // tile edge of every tiled algorithm (internal matrices are padded to it)
+
+inline int round_up(int n, int m) { return (n + m - 1) / m * m; }
+
+// One tile task of the batched DMMA GEMM: C[c_r.., c_c..] = beta*C0 + alpha * sum_k A * B^T-like
+// product over k_len elements of the contraction index.  Coordinates are element offsets inside
+// the (padded) matrices; how k advances through A and B depends on the kernel's layout template.
+struct TileTask {
+  int a_r, a_c;  // start of the A operand (row, col) in its stored matrix
+  int b_r, b_c;  // start of the B operand
+  int c_r, c_c;  // output tile origin
+  int k_len;     // contraction length (multiple of 16)
+  int flags;     // bit0: diagonal tile of a symmetric result (trace epilogue weight 1 instead of 2)
+};
+
+struct MatRef {
+  double *p;
+  long long ld;
+  long long stride;  // batch stride in doubles
+};
+
+struct GemmParams {
+  MatRef A, B, C, C0;  // C0.p == nullptr -> no addend
+  double alpha, beta;
+  const TileTask *tasks;
+  // trace epilogue (EPI_TRACE)
+  const double *x;  long long x_stride;      // inputs (per batch)
+  const double *avec; long long a_stride;    // a = K^-1 y (padded length np)
+  const double *theta;                       // B x 3 (alpha, rho, sigma)
+  double *partial;                           // B x ntasks x 4
+  int n;                                     // true matrix size (mask for the padding)
+  int ntasks;
+};
+
+struct Handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int device_ptrs = 0;
+  long long launches = 0;
+  long long ws_limit = 0;
+  char err[512] = {0};
+  // grow-only device workspace
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  // cached device-side task lists keyed by (kind, nt)
+  std::map<long long, std::pair<TileTask *, std::vector<int>>> task_cache;
+  // pinned staging for small host<->device scalars
+  double *pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+#define GPB_CUDA(h, call)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      snprintf((h)->err, sizeof((h)->err), "%s failed: %s (%s:%d)", #call,                    \
+               cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+      return -1000;                                                                           \
+    }                                                                                         \
+  } while (0)
+
+#define GPB_LAUNCH_CHECK(h)                                                                   \
+  do {                                                                                        \
+    (h)->launches++;                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) {                                                                 \
+      snprintf((h)->err, sizeof((h)->err), "kernel launch failed: %s (%s:%d)",                \
+               cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+      return -1001;                                                                           \
+    }                                                                                         \
+  } while (0)
+
+// ---- launchers implemented in the .cu files --------------------------------------------------
+enum GemmLayout { LAYOUT_NT = 0, LAYOUT_TN = 1, LAYOUT_NN = 2 };
+enum GemmEpi { EPI_AXPBY = 0, EPI_TRACE = 1 };
+
+int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch);
+int gemm_smem_setup(Handle *h);
+
+// panel kernels (panel.cu)
+int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n,
+                      int batch, int *info);
+int launch_trsm_tiles(Handle *h, double *L, long long ld, long long stride, int tile_col,
+                      int ntiles_below, int batch);
+int launch_tile_inverse(Handle *h, const double *L, double *W, long long ld, long long stride,
+                        int ntiles, int batch);
+int panel_smem_setup(Handle *h);
+
+}  // namespace gpb

@@ -1,0 +1,269 @@
+// Batched FP64 tensor-core (DMMA) tile GEMM for sm_100a.
+//
+// One CTA computes one 128x128 output tile of one matrix of the batch from a task list
+// (blockIdx.x = task, blockIdx.y = batch item).  The contraction streams 16-wide k-chunks of both
+// operands through a 4-stage cp.async (LDGSTS) pipeline into padded shared memory; fragments are
+// read conflict-free (leading dimensions == 4 mod 16 doubles) and fed to
+// mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- tcgen05 has no FP64 kind, so this IS the FP64
+// tensor path on B200; measured peak 37.0 TFLOP/s, profiles/fp64_peak_r01.json).
+// 8 warps, warp tile 64(m) x 32(n): 32 DMMAs per 12 shared-memory fragment loads.
+//
+// The mma is used "transposed" (mma rows <-> n, mma cols <-> m) so that each thread's two
+// accumulator values are adjacent in the column-major output: 16-byte global accesses.
+//
+// This kernel carries every O(N^3) stage of the path:
+//   NT  C = C0 - A B^T          left-looking Cholesky block-column update (replaces the inside of
+//                               Eigen LLT under cholesky_decompose, fit_hyperparameters.stan:25)
+//   NN  T = L21 W11, W21 = -W22 T   recursive triangular inverse (K^-1 for the gradient)
+//   TN  G = W^T W  + fused trace epilogue  0.5 tr((a a^T - K^-1) dK/dtheta)  (the reverse sweep
+//                               of multi_normal_cholesky -> cholesky_decompose -> cov_exp_quad)
+#include "common.cuh"
+
+namespace gpb {
+
+constexpr int KC = 16;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;
+constexpr int LD_MC = TILE + 4;  // operand with the tile index contiguous: stage[KC][132]
+constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
+constexpr int STAGE_DOUBLES = TILE * LD_KC;  // 2560 >= KC * LD_MC = 2112
+constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * (int)sizeof(double);  // 163840
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+template <bool A_KC, bool B_KC, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const TileTask task = p.tasks[blockIdx.x];
+  const long long b = blockIdx.y;
+  const double *__restrict__ A = p.A.p + b * p.A.stride;
+  const double *__restrict__ Bm = p.B.p + b * p.B.stride;
+  const long long lda = p.A.ld, ldb = p.B.ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+
+  double acc[4][8][2];
+#pragma unroll
+  for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) acc[ni][mi][0] = acc[ni][mi][1] = 0.0;
+
+  const int nk = task.k_len / KC;
+
+  // per-thread copy descriptors: 4 x 16B for A and 4 x 16B for B per stage
+  const double *srcA[4], *srcB[4];
+  int dstA[4], dstB[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int idx = tid + NTHREADS * r;
+    if (!A_KC) {
+      const int k = idx >> 6, m2 = idx & 63;
+      srcA[r] = A + (task.a_r + 2 * m2) + (long long)(task.a_c + k) * lda;
+      dstA[r] = k * LD_MC + 2 * m2;
+    } else {
+      const int m = idx >> 3, k2 = idx & 7;
+      srcA[r] = A + (task.a_r + 2 * k2) + (long long)(task.a_c + m) * lda;
+      dstA[r] = m * LD_KC + 2 * k2;
+    }
+    if (!B_KC) {
+      const int k = idx >> 6, n2 = idx & 63;
+      srcB[r] = Bm + (task.b_r + 2 * n2) + (long long)(task.b_c + k) * ldb;
+      dstB[r] = k * LD_MC + 2 * n2;
+    } else {
+      const int n = idx >> 3, k2 = idx & 7;
+      srcB[r] = Bm + (task.b_r + 2 * k2) + (long long)(task.b_c + n) * ldb;
+      dstB[r] = n * LD_KC + 2 * k2;
+    }
+  }
+  const long long stepA = A_KC ? (long long)KC : (long long)KC * lda;
+  const long long stepB = B_KC ? (long long)KC : (long long)KC * ldb;
+
+  auto load_stage = [&](int stage) {
+    double *sA = smem + stage * 2 * STAGE_DOUBLES;
+    double *sB = sA + STAGE_DOUBLES;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      cp_async16(sA + dstA[r], srcA[r]);
+      srcA[r] += stepA;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      cp_async16(sB + dstB[r], srcB[r]);
+      srcB[r] += stepB;
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nk) load_stage(s);
+    cp_async_commit();
+  }
+
+  for (int kc = 0; kc < nk; kc++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (kc + STAGES - 1 < nk) load_stage((kc + STAGES - 1) % STAGES);
+    cp_async_commit();
+
+    const double *sA = smem + (kc % STAGES) * 2 * STAGE_DOUBLES;
+    const double *sB = sA + STAGE_DOUBLES;
+#pragma unroll
+    for (int kk = 0; kk < KC / 4; kk++) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+        af[mi] = A_KC ? sA[(wm + mi * 8 + g) * LD_KC + kk * 4 + t] : sA[(kk * 4 + t) * LD_MC + wm + mi * 8 + g];
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++)
+        bf[ni] = B_KC ? sB[(wn + ni * 8 + g) * LD_KC + kk * 4 + t] : sB[(kk * 4 + t) * LD_MC + wn + ni * 8 + g];
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) dmma884(acc[ni][mi], bf[ni], af[mi]);
+    }
+  }
+  cp_async_wait<0>();
+
+  if (EPI == EPI_AXPBY) {
+    double *__restrict__ C = p.C.p + b * p.C.stride;
+    const double *__restrict__ C0 = p.C0.p ? p.C0.p + b * p.C0.stride : nullptr;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const int n = task.c_c + wn + ni * 8 + g;
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        const int m = task.c_r + wm + mi * 8 + 2 * t;
+        double2 v = make_double2(alpha * acc[ni][mi][0], alpha * acc[ni][mi][1]);
+        if (C0) {
+          const double2 c0 = *reinterpret_cast<const double2 *>(C0 + m + (long long)n * p.C0.ld);
+          v.x = fma(beta, c0.x, v.x);
+          v.y = fma(beta, c0.y, v.y);
+        }
+        *reinterpret_cast<double2 *>(C + m + (long long)n * p.C.ld) = v;
+      }
+    }
+  } else {
+    // ---- fused trace epilogue: this tile of G = K^-1 never has to reach HBM -----------------
+    __syncthreads();  // everyone is done with the pipeline buffers
+    double *xr = smem, *xc = smem + TILE, *ar = smem + 2 * TILE, *ac = smem + 3 * TILE;
+    double *red = smem + 4 * TILE;
+    const double *x = p.x + b * p.x_stride;
+    const double *av = p.avec + b * p.a_stride;
+    if (tid < TILE) {
+      const int i = task.c_r + tid;
+      xr[tid] = (i < p.n) ? x[i] : 0.0;
+      ar[tid] = (i < p.n) ? av[i] : 0.0;
+    } else {
+      const int j = task.c_c + tid - TILE;
+      xc[tid - TILE] = (j < p.n) ? x[j] : 0.0;
+      ac[tid - TILE] = (j < p.n) ? av[j] : 0.0;
+    }
+    __syncthreads();
+    const double rho = p.theta[b * 3 + 1];
+    const double nh = -0.5 / (rho * rho);
+    const bool diag_tile = (task.flags & 1) != 0;
+    double s_se = 0.0, s_d2 = 0.0, s_tr = 0.0;
+    double *__restrict__ C = p.C.p ? p.C.p + b * p.C.stride : nullptr;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const int nl = wn + ni * 8 + g;
+      const int j = task.c_c + nl;
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int ml = wm + mi * 8 + 2 * t + e;
+          const int i = task.c_r + ml;
+          const double G = acc[ni][mi][e];
+          if (i < p.n && j < p.n) {
+            const double d = xr[ml] - xc[nl];
+            const double d2 = d * d;
+            const double ek = exp(d2 * nh);
+            const double M = ar[ml] * ac[nl] - G;
+            s_se += M * ek;
+            s_d2 += M * ek * d2;
+            if (diag_tile && i == j) s_tr += G;
+          }
+        }
+        if (C) {
+          const int m = task.c_r + wm + mi * 8 + 2 * t;
+          *reinterpret_cast<double2 *>(C + m + (long long)j * p.C.ld) =
+              make_double2(acc[ni][mi][0], acc[ni][mi][1]);
+        }
+      }
+    }
+    const double w = diag_tile ? 1.0 : 2.0;
+    s_se *= w;
+    s_d2 *= w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_se += __shfl_xor_sync(0xffffffffu, s_se, o);
+      s_d2 += __shfl_xor_sync(0xffffffffu, s_d2, o);
+      s_tr += __shfl_xor_sync(0xffffffffu, s_tr, o);
+    }
+    if (lane == 0) {
+      red[warp * 3 + 0] = s_se;
+      red[warp * 3 + 1] = s_d2;
+      red[warp * 3 + 2] = s_tr;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double r0 = 0, r1 = 0, r2 = 0;
+      for (int w8 = 0; w8 < NTHREADS / 32; w8++) {
+        r0 += red[w8 * 3 + 0];
+        r1 += red[w8 * 3 + 1];
+        r2 += red[w8 * 3 + 2];
+      }
+      double *o = p.partial + ((long long)b * p.ntasks + blockIdx.x) * 4;
+      o[0] = r0;
+      o[1] = r1;
+      o[2] = r2;
+      o[3] = 0.0;
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC, int EPI>
+static int launch_one(Handle *h, const GemmParams &p, int ntasks, int batch) {
+  static bool configured = false;
+  auto kern = gemm_tile_kernel<A_KC, B_KC, EPI>;
+  if (!configured) {
+    GPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(ntasks, batch);
+  kern<<<grid, NTHREADS, GEMM_SMEM_BYTES, h->stream>>>(p);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
+  if (ntasks <= 0 || batch <= 0) return 0;
+  if (epi == EPI_AXPBY) {
+    switch (layout) {
+      case LAYOUT_NT: return launch_one<false, false, EPI_AXPBY>(h, p, ntasks, batch);
+      case LAYOUT_TN: return launch_one<true, true, EPI_AXPBY>(h, p, ntasks, batch);
+      case LAYOUT_NN: return launch_one<false, true, EPI_AXPBY>(h, p, ntasks, batch);
+    }
+  } else {
+    if (layout == LAYOUT_TN) return launch_one<true, true, EPI_TRACE>(h, p, ntasks, batch);
+  }
+  snprintf(h->err, sizeof(h->err), "launch_gemm: unsupported layout/epilogue %d/%d", (int)layout, (int)epi);
+  return -2;
+}
+
+}  // namespace gpb

@@ -1,0 +1,244 @@
+// Covariance (Gram) assembly kernels for sm_100a: coalesced 16-byte stores, inputs staged in shared
+// memory, noise/jitter diagonal fused.  HBM-write bound when K is materialised (8 N^2 bytes).
+//
+// Reference semantics restated here (not copied):
+//   cov_exp_quad + diagonal add     models/fit_hyperparameters.stan:19-24, exact_gp.stan:17-22
+//   rbf Gram and its l-tangent      covariance.cpp:15-25 (value) and the fvar tangent it seeds (:13)
+//   nine derivative kernels         derivative_kernels.R:39-73 ; R/kernels.R:19-32 (incl. the :31 quirk)
+//   joint (y, y', y'') covariance   design_notes.Rmd:6-46 ; R/ode_gp_library.R:29-30
+#include "common.cuh"
+#include "gram.cuh"
+
+namespace gpb {
+
+// value of one derivative kernel; operation order follows derivative_kernels.R:39-73
+__device__ __forceinline__ double kern_value(int kind, double tj, double tk, double l, double amp2) {
+  double d;
+  int base = kind;
+  if (kind == K_RQ) { d = tk - tj; base = K_QR; }
+  else if (kind == K_TQ) { d = tk - tj; base = K_QT; }
+  else if (kind == K_TR) { d = tk - tj; base = K_RT; }
+  else d = tj - tk;
+  const double l2 = l * l;
+  const double e = exp(-((d * d) / (2.0 * l2)));
+  const double l4 = l2 * l2;
+  switch (base) {
+    case K_QQ: return amp2 * e;
+    case K_QR: return amp2 * ((e * d) / l2);
+    case K_RR: return amp2 * (e / l2 - (e * d * d) / l4);
+    case K_RR_QUIRK: return amp2 * e / l2 - (e * d * d) / l4;  // R/kernels.R:31
+    case K_QT: return amp2 * (-(e / l2) + (e * d * d) / l4);
+    case K_RT: { const double l6 = l4 * l2; return amp2 * ((3.0 * e * d) / l4 - (e * d * d * d) / l6); }
+    case K_TT: { const double l6 = l4 * l2, l8 = l4 * l4;
+                 return amp2 * ((3.0 * e) / l4 - (6.0 * e * d * d) / l6 + (e * d * d * d * d) / l8); }
+    default: return 0.0;
+  }
+}
+
+// ---- element-wise evaluation (the R closures) ------------------------------------------------
+__global__ void kernel_eval_kernel(int kind, long long len, const double *__restrict__ tj,
+                                   const double *__restrict__ tk, double amp2, double l, double *__restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
+    out[i] = kern_value(kind, tj[i], tk[i], l, amp2);
+}
+
+// ---- generic outer(x, y, kind): n x m, tile 128x128 per CTA, two rows per thread -------------
+__global__ void __launch_bounds__(256) gram_outer_kernel(int kind, int n, int m, const double *__restrict__ x,
+                                                        const double *__restrict__ y, double amp2, double l,
+                                                        double *__restrict__ K, long long ldk) {
+  __shared__ double xs[TILE], ys[TILE];
+  const int r0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE, tid = threadIdx.x;
+  if (tid < TILE) xs[tid] = (r0 + tid < n) ? x[r0 + tid] : 0.0;
+  else ys[tid - TILE] = (c0 + tid - TILE < m) ? y[c0 + tid - TILE] : 0.0;
+  __syncthreads();
+  const int rl = 2 * (tid & 63), cq = tid >> 6;
+  const int i = r0 + rl;
+  const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+  for (int s = 0; s < 32; s++) {
+    const int cl = cq + 4 * s, j = c0 + cl;
+    if (j >= m) break;
+    const double v0 = kern_value(kind, xs[rl], ys[cl], l, amp2);
+    const double v1 = kern_value(kind, xs[rl + 1], ys[cl], l, amp2);
+    double *dst = K + i + (long long)j * ldk;
+    if (i + 1 < n && vec_ok) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+    else {
+      if (i < n) dst[0] = v0;
+      if (i + 1 < n) dst[1] = v1;
+    }
+  }
+}
+
+// ---- batched padded SE Gram for the fused LML path: K = alpha^2 exp(-0.5 d^2/rho^2) + c I -------
+// Internal layout: np x np (np multiple of 128) per item, identity in the padding so that the
+// padded factor is [L 0; 0 I].  Only tiles with tile_row >= tile_col are produced when lower_only.
+__global__ void __launch_bounds__(256) gram_se_batched_kernel(int n, int np, const double *__restrict__ x,
+                                                             long long x_stride, const double *__restrict__ theta,
+                                                             double jitter, int lower_only,
+                                                             double *__restrict__ K, long long stride) {
+  const int nt = np / TILE;
+  const int tr = blockIdx.x % nt, tc = blockIdx.x / nt;
+  if (lower_only && tr < tc) return;
+  __shared__ double xs[TILE], ys[TILE];
+  const long long b = blockIdx.y;
+  const double *xb = x + b * x_stride;
+  const int r0 = tr * TILE, c0 = tc * TILE, tid = threadIdx.x;
+  if (tid < TILE) xs[tid] = (r0 + tid < n) ? xb[r0 + tid] : 0.0;
+  else ys[tid - TILE] = (c0 + tid - TILE < n) ? xb[c0 + tid - TILE] : 0.0;
+  __syncthreads();
+  const double alpha = theta[b * 3 + 0], rho = theta[b * 3 + 1], sigma = theta[b * 3 + 2];
+  const double a2 = alpha * alpha, nh = -0.5 / (rho * rho), dadd = sigma * sigma + jitter;
+  double *Kb = K + b * stride;
+  const int rl = 2 * (tid & 63), cq = tid >> 6;
+#pragma unroll 4
+  for (int s = 0; s < 32; s++) {
+    const int cl = cq + 4 * s;
+    const int j = c0 + cl;
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = r0 + rl + e;
+      if (i < n && j < n) {
+        const double d = xs[rl + e] - ys[cl];
+        v[e] = (i == j) ? a2 + dadd : a2 * exp(d * d * nh);
+      } else {
+        v[e] = (i == j) ? 1.0 : 0.0;
+      }
+    }
+    *reinterpret_cast<double2 *>(Kb + (r0 + rl) + (long long)j * np) = make_double2(v[0], v[1]);
+  }
+}
+
+// ---- rbf_cov_chol Gram + tangent (covariance.cpp:15-25): padded, full square -------------------
+__global__ void __launch_bounds__(256) gram_rbf_tangent_kernel(int n, int np, const double *__restrict__ x, double l,
+                                                              double jitter, double *__restrict__ S,
+                                                              double *__restrict__ Sdot) {
+  __shared__ double xs[TILE], ys[TILE];
+  const int r0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE, tid = threadIdx.x;
+  if (tid < TILE) xs[tid] = (r0 + tid < n) ? x[r0 + tid] : 0.0;
+  else ys[tid - TILE] = (c0 + tid - TILE < n) ? x[c0 + tid - TILE] : 0.0;
+  __syncthreads();
+  const double two_l2 = 2.0 * l * l, l3 = l * l * l;
+  const int rl = 2 * (tid & 63), cq = tid >> 6;
+  for (int s = 0; s < 32; s++) {
+    const int cl = cq + 4 * s, j = c0 + cl;
+    double v[2], dv[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = r0 + rl + e;
+      if (i < n && j < n) {
+        const double d = xs[rl + e] - ys[cl];
+        const double ev = exp(-(d * d) / two_l2);
+        v[e] = ev + ((i == j) ? jitter : 0.0);
+        dv[e] = ev * d * d / l3;
+      } else {
+        v[e] = (i == j) ? 1.0 : 0.0;
+        dv[e] = 0.0;
+      }
+    }
+    *reinterpret_cast<double2 *>(S + (r0 + rl) + (long long)j * np) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2 *>(Sdot + (r0 + rl) + (long long)j * np) = make_double2(dv[0], dv[1]);
+  }
+}
+
+// ---- joint derivative-observation covariance ---------------------------------------------------
+__constant__ int c_joint_kind[3][3] = {{K_QQ, K_QR, K_QT}, {K_RQ, K_RR, K_RT}, {K_TQ, K_TR, K_TT}};
+
+__global__ void __launch_bounds__(256) gram_deriv_kernel(int n, int nblocks, const double *__restrict__ t, double alpha,
+                                                        double rho, double n0, double n1, double n2, double jitter,
+                                                        int quirk, double *__restrict__ K, long long ldk) {
+  const int N = n * nblocks;
+  const int r0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE, tid = threadIdx.x;
+  const double amp2 = alpha * alpha;
+  const double noise2[3] = {n0 * n0, n1 * n1, n2 * n2};
+  const int rl = tid & 127, ch = tid >> 7;
+  const int I = r0 + rl;
+  if (I >= N) return;
+  const int bi = I / n, i = I - bi * n;
+  const double ti = t[i];
+  for (int s = 0; s < 64; s++) {
+    const int J = c0 + ch + 2 * s;
+    if (J >= N) break;
+    const int bj = J / n, j = J - bj * n;
+    int kind = c_joint_kind[bi][bj];
+    if (quirk && kind == K_RR) kind = K_RR_QUIRK;
+    double v = kern_value(kind, ti, t[j], rho, amp2);
+    if (I == J) v += noise2[bi] + jitter;
+    K[I + (long long)J * ldk] = v;
+  }
+}
+
+// ---- QQard (R/kernels.R:19) ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_ard_kernel(int n, int m, int D, const double *__restrict__ X, long long ldx,
+                                                      const double *__restrict__ Y, long long ldy, double alpha,
+                                                      const double *__restrict__ rho, int rho_len,
+                                                      double *__restrict__ K, long long ldk) {
+  const int i = blockIdx.x * 128 + (threadIdx.x & 127);
+  const int jh = threadIdx.x >> 7;
+  if (i >= n) return;
+  const double a2 = alpha * alpha;
+  for (int j = blockIdx.y * 64 + jh; j < min(m, (int)(blockIdx.y + 1) * 64); j += 2) {
+    double s = 0.0;
+    for (int d = 0; d < D; d++) {
+      const double q = (X[i + d * ldx] - Y[j + d * ldy]) / rho[rho_len == 1 ? 0 : d];
+      s += q * q;
+    }
+    K[i + (long long)j * ldk] = a2 * exp(-0.5 * s);
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+int launch_kernel_eval(Handle *h, int kind, long long len, const double *tj, const double *tk, double amp2,
+                       double l, double *out) {
+  if (len <= 0) return 0;
+  const int blocks = (int)((len + 255) / 256 > 148 * 16 ? 148 * 16 : (len + 255) / 256);
+  kernel_eval_kernel<<<blocks, 256, 0, h->stream>>>(kind, len, tj, tk, amp2, l, out);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gram_outer(Handle *h, int kind, int n, int m, const double *x, const double *y, double amp2, double l,
+                      double *K, long long ldk) {
+  if (n <= 0 || m <= 0) return 0;
+  dim3 grid((n + TILE - 1) / TILE, (m + TILE - 1) / TILE);
+  gram_outer_kernel<<<grid, 256, 0, h->stream>>>(kind, n, m, x, y, amp2, l, K, ldk);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gram_se_batched(Handle *h, int n, int np, const double *x, long long x_stride, const double *theta,
+                           double jitter, int lower_only, double *K, long long stride, int batch) {
+  const int nt = np / TILE;
+  dim3 grid(nt * nt, batch);
+  gram_se_batched_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, x_stride, theta, jitter, lower_only, K, stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gram_rbf_tangent(Handle *h, int n, int np, const double *x, double l, double jitter, double *S,
+                            double *Sdot) {
+  dim3 grid(np / TILE, np / TILE);
+  gram_rbf_tangent_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, l, jitter, S, Sdot);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gram_deriv(Handle *h, int n, int nblocks, const double *t, double alpha, double rho, const double *noise,
+                      double jitter, int quirk, double *K, long long ldk) {
+  const int N = n * nblocks;
+  dim3 grid((N + TILE - 1) / TILE, (N + TILE - 1) / TILE);
+  gram_deriv_kernel<<<grid, 256, 0, h->stream>>>(n, nblocks, t, alpha, rho, noise[0], nblocks > 1 ? noise[1] : 0.0,
+                                                nblocks > 2 ? noise[2] : 0.0, jitter, quirk, K, ldk);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gram_ard(Handle *h, int n, int m, int D, const double *X, long long ldx, const double *Y, long long ldy,
+                    double alpha, const double *rho, int rho_len, double *K, long long ldk) {
+  if (n <= 0 || m <= 0) return 0;
+  dim3 grid((n + 127) / 128, (m + 63) / 64);
+  gram_ard_kernel<<<grid, 256, 0, h->stream>>>(n, m, D, X, ldx, Y, ldy, alpha, rho, rho_len, K, ldk);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+}  // namespace gpb

@@ -1,0 +1,42 @@
+// Kernel-kind ids (match include/gpb200.h) and launchers of gram.cu / solve.cu.
+#pragma once
+#include "common.cuh"
+
+namespace gpb {
+
+enum { K_QQ = 0, K_QR = 1, K_RQ = 2, K_RR = 3, K_QT = 4, K_TQ = 5, K_RT = 6, K_TR = 7, K_TT = 8, K_RR_QUIRK = 9 };
+
+int launch_kernel_eval(Handle *h, int kind, long long len, const double *tj, const double *tk, double amp2,
+                       double l, double *out);
+int launch_gram_outer(Handle *h, int kind, int n, int m, const double *x, const double *y, double amp2, double l,
+                      double *K, long long ldk);
+int launch_gram_se_batched(Handle *h, int n, int np, const double *x, long long x_stride, const double *theta,
+                           double jitter, int lower_only, double *K, long long stride, int batch);
+int launch_gram_rbf_tangent(Handle *h, int n, int np, const double *x, double l, double jitter, double *S,
+                            double *Sdot);
+int launch_gram_deriv(Handle *h, int n, int nblocks, const double *t, double alpha, double rho, const double *noise,
+                      double jitter, int quirk, double *K, long long ldk);
+int launch_gram_ard(Handle *h, int n, int m, int D, const double *X, long long ldx, const double *Y, long long ldy,
+                    double alpha, const double *rho, int rho_len, double *K, long long ldk);
+
+// solve.cu
+int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, const double *y, long long y_stride,
+                        int n_valid, double *z, long long z_stride, int batch);
+int launch_trmv_lower_t(Handle *h, int np, const double *W, long long stride, const double *z, long long z_stride,
+                        double *a, long long a_stride, int batch);
+int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
+                        long long y_stride, const double *mu, int n_valid, double *z, long long z_stride, int batch);
+int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec, const double *z, const double *a,
+                    const double *partial, int ntasks, const double *theta, double *lml, double *grad, int batch);
+int launch_pack(Handle *h, int rows, int cols, const double *src, long long lds, int rp, int cp, double *dst,
+                int mode, double diag_add);
+int launch_unpack(Handle *h, int rows, int cols, const double *src, long long lds_src, double *dst, long long ldd,
+                  int mode, double diag_add);
+int launch_phi_lower(Handle *h, int np, double *A);
+int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv, const double *z, const double *add,
+                  double *out);
+int launch_hermite(Handle *h, long long len, int n, const double *y1, const double *y2, const double *k1,
+                   const double *k2, double x1, double x2, double l, double *v, double *dvdl);
+int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2);
+
+}  // namespace gpb

@@ -1,0 +1,365 @@
+// HBM-bound pieces of the path (sm_100a): triangular mat-vecs and solves with warp-shuffle
+// reductions, the deterministic LML/gradient finalisation, pack/unpack between caller matrices and
+// the padded internal layout, Hermite interpolation of tabulated factors.
+//
+//   trmv_lower_n / trmv_lower_t   z = W y, a = W^T z   (and f = L z of exact_gp.stan:25)
+//   trsv_blocked                  mdivide_left_tri_low inside multi_normal_cholesky
+//                                 (models/fit_hyperparameters.stan:31) when no inverse is wanted
+//   finalize                      lml = -n/2 log 2pi - sum log L_ii - 0.5 ||z||^2 and the three
+//                                 gradient components from the fused trace partials
+//   hermite                       covariance.cpp:63-66,85-88 / cubic_interpolated_gp.hpp:63-70
+#include "common.cuh"
+#include "gram.cuh"
+
+namespace gpb {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// z[i] = sum_{k<=i} W[i,k] y[k] for one 128-row strip per CTA.  The strict upper triangle of the
+// diagonal tile is zero by construction, so the strip is read as a dense 128 x (tile+1)*128 block.
+__global__ void __launch_bounds__(256) trmv_lower_n_kernel(int np, const double *__restrict__ W, long long stride,
+                                                          const double *__restrict__ y, long long y_stride,
+                                                          int n_valid, double *__restrict__ z, long long z_stride) {
+  __shared__ double part[TILE];
+  __shared__ double ys[512];
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const long long b = blockIdx.y;
+  const double *Wb = W + b * stride;
+  const double *yb = y + b * y_stride;
+  const int r = tid & 127, half = tid >> 7;
+  const int kmax = (tile + 1) * TILE;
+  const int i = tile * TILE + r;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int k0 = 0; k0 < kmax; k0 += 512) {
+    __syncthreads();
+    for (int q = tid; q < 512; q += 256) ys[q] = (k0 + q < n_valid) ? yb[k0 + q] : 0.0;
+    __syncthreads();
+    const int kend = min(512, kmax - k0);
+    const double *wp = Wb + i + (long long)(k0 + half) * np;
+#pragma unroll 4
+    for (int k = half; k < kend; k += 8) {
+      s0 = fma(wp[0], ys[k], s0);
+      s1 = fma(wp[2LL * np], ys[k + 2], s1);
+      s2 = fma(wp[4LL * np], ys[k + 4], s2);
+      s3 = fma(wp[6LL * np], ys[k + 6], s3);
+      wp += 8LL * np;
+    }
+  }
+  const double s = (s0 + s1) + (s2 + s3);
+  if (half == 1) part[r] = s;
+  __syncthreads();
+  if (half == 0) z[b * z_stride + i] = s + part[r];
+}
+
+// a[k] = sum_{i>=k} W[i,k] z[i]; one warp per column, 16-byte loads, shuffle reduction.
+__global__ void __launch_bounds__(256) trmv_lower_t_kernel(int np, const double *__restrict__ W, long long stride,
+                                                          const double *__restrict__ z, long long z_stride,
+                                                          double *__restrict__ a, long long a_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
+  const long long b = blockIdx.y;
+  const double *col = W + b * stride + (long long)k * np;
+  const double *zb = z + b * z_stride;
+  const int istart = (k / TILE) * TILE;
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = istart + 2 * lane; i < np; i += 64) {
+    const double2 w = *reinterpret_cast<const double2 *>(col + i);
+    const double2 zz = *reinterpret_cast<const double2 *>(zb + i);
+    s0 = fma(w.x, zz.x, s0);
+    s1 = fma(w.y, zz.y, s1);
+  }
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) a[b * a_stride + k] = s;
+}
+
+// Blocked forward substitution L z = (y - mu), one CTA per batch item.  Per 128-row block:
+// s = rhs_j - L[j, 0:j] z[0:j] (two k-halves per row), then z_j = Wdiag_j s with the pre-inverted
+// diagonal tile.
+__global__ void __launch_bounds__(256) trsv_blocked_kernel(int np, const double *__restrict__ L,
+                                                          const double *__restrict__ Wdiag, long long stride,
+                                                          const double *__restrict__ y, long long y_stride,
+                                                          const double *__restrict__ mu, int n_valid,
+                                                          double *__restrict__ z, long long z_stride) {
+  extern __shared__ double zs[];  // np + 2*128
+  double *part = zs + np;
+  double *sv = part + TILE;
+  const long long b = blockIdx.x;
+  const double *Lb = L + b * stride, *Wb = Wdiag + b * stride;
+  const double *yb = y + b * y_stride;
+  const int tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+  const int nt = np / TILE;
+  for (int j = 0; j < nt; j++) {
+    const int i = j * TILE + r;
+    const int kmax = j * TILE;
+    double s0 = 0.0, s1 = 0.0;
+    const double *lp = Lb + i + (long long)half * np;
+    for (int k = half; k < kmax; k += 4) {
+      s0 = fma(lp[0], zs[k], s0);
+      s1 = fma(lp[2LL * np], zs[k + 2], s1);
+      lp += 4LL * np;
+    }
+    if (half == 1) part[r] = s0 + s1;
+    __syncthreads();
+    if (half == 0) {
+      double rhs = 0.0;
+      if (i < n_valid) rhs = yb[i] - (mu ? mu[i] : 0.0);
+      sv[r] = rhs - (s0 + s1 + part[r]);
+    }
+    __syncthreads();
+    // z_j = Wdiag_j * sv  (lower-triangular 128x128, strict upper is zero)
+    const double *wd = Wb + (long long)j * TILE * (np + 1);
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = half; k < TILE; k += 4) {
+      t0 = fma(wd[r + (long long)k * np], sv[k], t0);
+      t1 = fma(wd[r + (long long)(k + 2) * np], sv[k + 2], t1);
+    }
+    if (half == 1) part[r] = t0 + t1;
+    __syncthreads();
+    if (half == 0) {
+      const double v = t0 + t1 + part[r];
+      zs[i] = v;
+      z[b * z_stride + i] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Deterministic finalisation, one CTA per batch item.
+__global__ void __launch_bounds__(256) finalize_kernel(int n, int np, int want_grad, const double *__restrict__ dvec,
+                                                      const double *__restrict__ z, const double *__restrict__ a,
+                                                      const double *__restrict__ partial, int ntasks,
+                                                      const double *__restrict__ theta, double *__restrict__ lml,
+                                                      double *__restrict__ grad) {
+  __shared__ double red[8][6];
+  const long long b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double ld = 0.0, qf = 0.0, aa = 0.0, p0 = 0.0, p1 = 0.0, p2 = 0.0;
+  for (int i = tid; i < n; i += 256) {
+    ld += log(dvec[b * np + i]);
+    const double zi = z[b * np + i];
+    qf = fma(zi, zi, qf);
+    if (want_grad) {
+      const double ai = a[b * np + i];
+      aa = fma(ai, ai, aa);
+    }
+  }
+  if (want_grad)
+    for (int q = tid; q < ntasks; q += 256) {
+      const double *pp = partial + (b * ntasks + q) * 4;
+      p0 += pp[0];
+      p1 += pp[1];
+      p2 += pp[2];
+    }
+  ld = warp_sum(ld); qf = warp_sum(qf); aa = warp_sum(aa);
+  p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+  if (lane == 0) {
+    red[warp][0] = ld; red[warp][1] = qf; red[warp][2] = aa;
+    red[warp][3] = p0; red[warp][4] = p1; red[warp][5] = p2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < 8; w++)
+      for (int q = 0; q < 6; q++) s[q] += red[w][q];
+    lml[b] = -0.5 * n * 1.8378770664093454835606594728112 - s[0] - 0.5 * s[1];
+    if (want_grad) {
+      const double alpha = theta[b * 3 + 0], rho = theta[b * 3 + 1], sigma = theta[b * 3 + 2];
+      grad[b * 3 + 0] = alpha * s[3];                                   // 0.5 sum M * 2 alpha e
+      grad[b * 3 + 1] = 0.5 * alpha * alpha * s[4] / (rho * rho * rho);  // 0.5 sum M * alpha^2 e d^2 / rho^3
+      grad[b * 3 + 2] = sigma * (s[2] - s[5]);                          // 0.5 tr(M) 2 sigma
+    }
+  }
+}
+
+// out2[0] = sum z_i^2, out2[1] = sum log L_ii  (multi_normal_cholesky_lpdf pieces)
+__global__ void __launch_bounds__(256) sumsq_logdiag_kernel(int n, const double *__restrict__ z,
+                                                           const double *__restrict__ L, long long ldl,
+                                                           double *__restrict__ out2) {
+  __shared__ double red[8][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double q = 0.0, ld = 0.0;
+  for (int i = tid; i < n; i += 256) {
+    q = fma(z[i], z[i], q);
+    ld += log(L[i + (long long)i * ldl]);
+  }
+  q = warp_sum(q); ld = warp_sum(ld);
+  if (lane == 0) { red[warp][0] = q; red[warp][1] = ld; }
+  __syncthreads();
+  if (tid == 0) {
+    double s0 = 0, s1 = 0;
+    for (int w = 0; w < 8; w++) { s0 += red[w][0]; s1 += red[w][1]; }
+    out2[0] = s0; out2[1] = s1;
+  }
+}
+
+// pack a caller matrix into the padded internal layout.
+// mode 0: dense, zero padding.  mode 1: square, identity on the padded diagonal, + diag_add on the
+// real diagonal.  mode 2: lower triangle only (strict upper zeroed), identity padding.
+__global__ void pack_kernel(int rows, int cols, const double *__restrict__ src, long long lds, int rp, int cp,
+                            double *__restrict__ dst, int mode, double diag_add) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= rp || j >= cp) return;
+  double v = 0.0;
+  if (i < rows && j < cols) {
+    v = src[i + (long long)j * lds];
+    if (mode == 1 && i == j) v += diag_add;
+    if (mode == 2 && i < j) v = 0.0;
+  } else if (mode != 0 && i == j) {
+    v = 1.0;
+  }
+  dst[i + (long long)j * rp] = v;
+}
+
+// unpack.  mode 0: dense.  mode 1: lower (strict upper zero).  mode 2: symmetric, mirrored from the
+// lower triangle.  diag_add is added on the diagonal.
+__global__ void unpack_kernel(int rows, int cols, const double *__restrict__ src, long long lds_src,
+                              double *__restrict__ dst, long long ldd, int mode, double diag_add) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= rows || j >= cols) return;
+  double v;
+  if (mode == 1) v = (i >= j) ? src[i + (long long)j * lds_src] : 0.0;
+  else if (mode == 2) v = (i >= j) ? src[i + (long long)j * lds_src] : src[j + (long long)i * lds_src];
+  else v = src[i + (long long)j * lds_src];
+  if (i == j) v += diag_add;
+  dst[i + (long long)j * ldd] = v;
+}
+
+// Phi for the forward-mode Cholesky tangent: keep the lower triangle, halve the diagonal, zero the
+// strict upper part (only the diagonal tiles contain upper entries that are ever read).
+__global__ void phi_lower_kernel(int np, double *__restrict__ A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= np) return;
+  if ((i / TILE) != (j / TILE)) return;
+  double *p = A + i + (long long)j * np;
+  if (i == j) *p *= 0.5;
+  else if (i < j) *p = 0.0;
+}
+
+// out[c] = add[c] + sum_r V[r,c] z[r]   (dense V^T z, warp per column)
+__global__ void __launch_bounds__(256) gemv_t_kernel(int rows, int cols, const double *__restrict__ V, long long ldv,
+                                                    const double *__restrict__ z, const double *__restrict__ add,
+                                                    double *__restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= cols) return;
+  double s = 0.0;
+  for (int r = lane; r < rows; r += 32) s = fma(V[r + (long long)c * ldv], z[r], s);
+  s = warp_sum(s);
+  if (lane == 0) out[c] = s + (add ? add[c] : 0.0);
+}
+
+// Cubic-Hermite interpolation between two tabulated factors (lower triangle only; n x n dense
+// column-major tables).  v -> interpolated L, dvdl -> its l-derivative (may be null).
+__global__ void hermite_kernel(long long len, int n, const double *__restrict__ y1, const double *__restrict__ y2,
+                               const double *__restrict__ k1, const double *__restrict__ k2, double x1, double x2,
+                               double l, double *__restrict__ v, double *__restrict__ dvdl) {
+  const double dx = x2 - x1, t = (l - x1) / dx, dtdl = 1.0 / dx;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < len; q += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(q % n), j = (int)(q / n);
+    double vv = 0.0, dd = 0.0;
+    if (j <= i) {
+      const double a1 = y1[q], a2 = y2[q];
+      const double a = k1[q] * dx - (a2 - a1);
+      const double bb = -k2[q] * dx + (a2 - a1);
+      vv = (1 - t) * a1 + t * a2 + t * (1 - t) * (a * (1 - t) + bb * t);
+      dd = (bb * (2 - 3 * t) * t + a * (1 + t * (-4 + 3 * t)) - a1 + a2) * dtdl;
+    }
+    v[q] = vv;
+    if (dvdl) dvdl[q] = dd;
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, const double *y, long long y_stride,
+                        int n_valid, double *z, long long z_stride, int batch) {
+  dim3 grid(np / TILE, batch);
+  trmv_lower_n_kernel<<<grid, 256, 0, h->stream>>>(np, W, stride, y, y_stride, n_valid, z, z_stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_trmv_lower_t(Handle *h, int np, const double *W, long long stride, const double *z, long long z_stride,
+                        double *a, long long a_stride, int batch) {
+  dim3 grid(np / 8, batch);
+  trmv_lower_t_kernel<<<grid, 256, 0, h->stream>>>(np, W, stride, z, z_stride, a, a_stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
+                        long long y_stride, const double *mu, int n_valid, double *z, long long z_stride, int batch) {
+  const size_t smem = (size_t)(np + 2 * TILE) * sizeof(double);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    GPB_CUDA(h, cudaFuncSetAttribute(trsv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  if (smem > 227 * 1024) {
+    snprintf(h->err, sizeof(h->err), "trsv_blocked: n too large for the shared-memory solution vector");
+    return -3;
+  }
+  trsv_blocked_kernel<<<batch, 256, smem, h->stream>>>(np, L, Wdiag, stride, y, y_stride, mu, n_valid, z, z_stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec, const double *z, const double *a,
+                    const double *partial, int ntasks, const double *theta, double *lml, double *grad, int batch) {
+  finalize_kernel<<<batch, 256, 0, h->stream>>>(n, np, want_grad, dvec, z, a, partial, ntasks, theta, lml, grad);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2) {
+  sumsq_logdiag_kernel<<<1, 256, 0, h->stream>>>(n, z, L, ldl, out2);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_pack(Handle *h, int rows, int cols, const double *src, long long lds, int rp, int cp, double *dst,
+                int mode, double diag_add) {
+  dim3 grid((rp + 255) / 256, cp);
+  pack_kernel<<<grid, 256, 0, h->stream>>>(rows, cols, src, lds, rp, cp, dst, mode, diag_add);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_unpack(Handle *h, int rows, int cols, const double *src, long long lds_src, double *dst, long long ldd,
+                  int mode, double diag_add) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((rows + 255) / 256, cols);
+  unpack_kernel<<<grid, 256, 0, h->stream>>>(rows, cols, src, lds_src, dst, ldd, mode, diag_add);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_phi_lower(Handle *h, int np, double *A) {
+  dim3 grid((np + 255) / 256, np);
+  phi_lower_kernel<<<grid, 256, 0, h->stream>>>(np, A);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv, const double *z, const double *add,
+                  double *out) {
+  gemv_t_kernel<<<(cols + 7) / 8, 256, 0, h->stream>>>(rows, cols, V, ldv, z, add, out);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_hermite(Handle *h, long long len, int n, const double *y1, const double *y2, const double *k1,
+                   const double *k2, double x1, double x2, double l, double *v, double *dvdl) {
+  const int blocks = (int)((len + 255) / 256 > 148 * 8 ? 148 * 8 : (len + 255) / 256);
+  hermite_kernel<<<blocks, 256, 0, h->stream>>>(len, n, y1, y2, k1, k2, x1, x2, l, v, dvdl);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+}  // namespace gpb

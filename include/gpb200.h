@@ -1,0 +1,152 @@
+/* gpb200.h -- C ABI of libgpb200.so: the B200-native (sm_100a) GP hot path that replaces the
+ * arithmetic behind bbbales2/gp's native and R-level entry points.
+ *
+ * Conventions (the ones R / Rcpp / Eigen use on the reference side):
+ *   - every matrix is COLUMN-MAJOR double with an explicit leading dimension;
+ *   - plain pointers and sizes only -- no R, Stan, Eigen or torch types cross this boundary;
+ *   - every call returns an int status: 0 = ok; k > 0 = the matrix is not positive definite and
+ *     k is the 1-based index of the first non-positive pivot (LAPACK convention; Stan Math's
+ *     cholesky_decompose throws std::domain_error in that case, the R shim raises an R error);
+ *     k < 0 = bad argument / CUDA failure, text available from gpb200_last_error();
+ *   - pointers are HOST pointers by default (R's memory); gpb200_set_pointer_mode(h, 1) makes all
+ *     DATA pointers device pointers (scalars passed by value stay by value; output scalars are
+ *     then device pointers too).  The library synchronises before returning in host mode; in
+ *     device mode work is enqueued on the handle's stream and the caller synchronises.
+ *   - theta is always (alpha, rho, sigma): amplitude, length-scale, noise sd  (the parameters of
+ *     models/fit_hyperparameters.stan:12-16).
+ *
+ * There is no CPU fallback: every entry point runs hand-written CUDA kernels and fails with a
+ * negative status if no sm_100 device is present.
+ *
+ * Reference citations are relative to the root of bbbales2/gp.
+ */
+#ifndef GPB200_H
+#define GPB200_H
+
+#if defined(__GNUC__)
+#define GPB200_API __attribute__((visibility("default")))
+#else
+#define GPB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpb200_handle_s *gpb200_handle_t;
+
+/* ---- handle ------------------------------------------------------------------------------- */
+GPB200_API int gpb200_create(gpb200_handle_t *h, int device);          /* one handle per GPU / host thread  */
+GPB200_API int gpb200_destroy(gpb200_handle_t h);
+GPB200_API int gpb200_set_stream(gpb200_handle_t h, void *cuda_stream); /* cudaStream_t; NULL = default      */
+GPB200_API int gpb200_set_pointer_mode(gpb200_handle_t h, int device_pointers);
+GPB200_API int gpb200_synchronize(gpb200_handle_t h);
+GPB200_API const char *gpb200_last_error(gpb200_handle_t h);
+GPB200_API long long gpb200_launch_count(gpb200_handle_t h);            /* kernels launched by this handle   */
+GPB200_API int gpb200_version(void);
+/* cap on the device workspace the batched entry points may allocate (bytes; 0 = 60% of free) */
+GPB200_API int gpb200_set_workspace_limit(gpb200_handle_t h, long long bytes);
+
+/* ---- a9: kernel functions ------------------------------------------------------------------ */
+/* kinds of derivative_kernels.R:39-73 (Q = value, R = first derivative, T = second derivative;
+ * first letter goes with tj) */
+enum { GPB200_QQ = 0, GPB200_QR = 1, GPB200_RQ = 2, GPB200_RR = 3, GPB200_QT = 4,
+       GPB200_TQ = 5, GPB200_RT = 6, GPB200_TR = 7, GPB200_TT = 8,
+       GPB200_RR_QUIRK = 9 /* R/kernels.R:30-32: amp2 multiplies only the first term */ };
+
+/* element-wise kernel: out[i] = amp2 * kind(tj[i], tk[i], l) -- the R closures
+ * QQ..TT(tj, tk, l) of derivative_kernels.R:39-73 (amp2 = 1) and gp_derivs.py:15-40 (amp2 = a^2) */
+GPB200_API int gpb200_kernel_eval(gpb200_handle_t h, int kind, long long len, const double *tj,
+                       const double *tk, double amp2, double l, double *out);
+
+/* outer(x, y, kind): K[i + j*ldk] = amp2 * kind(x[i], y[j], l), n x m.  Replaces
+ * outer(ti, ti, FUN = kern) (pendulum_fit.R:238-240), QQ/QR/RR(x, y, phi) of R/kernels.R:22-32
+ * (amp2 = phi1^2, l = phi2) and cov() of gp_derivs.py:76-83. */
+GPB200_API int gpb200_gram_outer(gpb200_handle_t h, int kind, int n, int m, const double *x, const double *y,
+                      double amp2, double l, double *K, int ldk);
+
+/* QQard (R/kernels.R:19): K[i,j] = alpha^2 exp(-0.5 sum_d ((X[i,d]-Y[j,d])/rho[d])^2);
+ * X is n x D, Y is m x D, both column-major (R matrices). */
+GPB200_API int gpb200_gram_ard(gpb200_handle_t h, int n, int m, int D, const double *X, int ldx,
+                    const double *Y, int ldy, double alpha, const double *rho, double *K, int ldk);
+
+/* cov_exp_quad(x, alpha, rho) + diag_add * I in one pass (models/fit_hyperparameters.stan:19-24,
+ * exact_gp.stan:17-22, covariance.cpp:15-25 with alpha = 1, diag_add = 1e-10). Full symmetric
+ * n x n output. */
+GPB200_API int gpb200_gram_se(gpb200_handle_t h, int n, const double *x, double alpha, double rho,
+                   double diag_add, double *K, int ldk);
+
+/* joint covariance of (y, y', y'') on one grid t (design_notes.Rmd:6-46; blocks
+ * {QQ,QR,QT;RQ,RR,RT;TQ,TR,TT} * alpha^2 + diag(noise[b]^2 + jitter)); nblocks in 1..3,
+ * output (nblocks*n)^2.  nblocks = 2, noise = (sigma, 0), jitter = 1e-6 is the matrix of
+ * R/ode_gp_library.R:29-30 (set quirk = 1 for R/kernels.R's RR). */
+GPB200_API int gpb200_gram_deriv(gpb200_handle_t h, int n, const double *t, double alpha, double rho,
+                      int nblocks, const double *noise, double jitter, int quirk, double *K,
+                      int ldk);
+
+/* ---- a6-a8: factorisation, solves, likelihood ------------------------------------------------ */
+/* cholesky_decompose (fit_hyperparameters.stan:25; covariance.cpp:29; R chol spectral_test.R:32):
+ * in place, lower; the strict upper triangle is zeroed like Eigen's matrixL(). */
+GPB200_API int gpb200_potrf(gpb200_handle_t h, int n, double *A, int lda);
+
+/* mdivide_left_tri_low (inside multi_normal_cholesky): B <- L^-1 B, n x nrhs */
+GPB200_API int gpb200_trsm_lower(gpb200_handle_t h, int n, int nrhs, const double *L, int ldl, double *B,
+                      int ldb);
+/* B <- (L L^T)^-1 B: solve(K, y), solve(K, KKs) (pendulum_fit.R:244,250) given the factor */
+GPB200_API int gpb200_potrs(gpb200_handle_t h, int n, int nrhs, const double *L, int ldl, double *B, int ldb);
+/* f = L z, lower-triangular (exact_gp.stan:25, heteroscedastic.stan:31-32) */
+GPB200_API int gpb200_trmv_lower(gpb200_handle_t h, int n, const double *L, int ldl, const double *z,
+                      double *f);
+/* multi_normal_cholesky_lpdf(y | mu, L) (fit_hyperparameters.stan:31); mu may be NULL (zeros);
+ * drop_constants != 0 omits -0.5 n log(2 pi) like Stan's `~` statement. */
+GPB200_API int gpb200_mvn_chol_lpdf(gpb200_handle_t h, int n, const double *y, const double *mu,
+                         const double *L, int ldl, int drop_constants, double *lp);
+
+/* ---- CS-A: fused Gram -> Cholesky -> LML + gradient ----------------------------------------- */
+/* One evaluation of the model block of models/fit_hyperparameters.stan:18-31 and of its reverse
+ * sweep: K = cov_exp_quad(x, alpha, rho) + (sigma^2 + jitter) I;
+ * lml = MVN(y | 0, K) with constants; grad = d lml / d (alpha, rho, sigma). */
+GPB200_API int gpb200_lml_grad(gpb200_handle_t h, int n, const double *x, const double *y,
+                    const double *theta, double jitter, double *lml, double *grad);
+
+/* B independent evaluations (hyper-parameter draws: pendulum_fit.R:259-268; per-group GPs:
+ * multiple_players.stan:59-63).  x, y: B strides in doubles (0 = one shared vector);
+ * theta: B x 3 row-major; outputs lml[B], grad[B*3], info[B] (per-item LAPACK-style status).
+ * want_grad = 0 skips the inverse (LML only, N^3/3 flops instead of N^3). */
+GPB200_API int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const double *x, long long x_stride,
+                            const double *y, long long y_stride, const double *theta,
+                            double jitter, int want_grad, double *lml, double *grad, int *info);
+
+/* ---- a1-a3: the reference's one native entry point ----------------------------------------- */
+/* Exact twin of rbf_cov_chol (covariance.cpp:9-47): Sigma = exp(-(xi-xj)^2/(2 l^2)) + 1e-10 I,
+ * L = chol(Sigma), dLdl = d L / d l (forward mode); both n x n column-major with zero strict
+ * upper triangle. */
+GPB200_API int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, double l, double *L,
+                        double *dLdl);
+
+/* approx_L (covariance.cpp:49-96): cubic-Hermite interpolation in l between tabulated factors;
+ * Ls / dLdls are P pointers to n x n column-major tables, lp the P grid points. */
+GPB200_API int gpb200_approx_L(gpb200_handle_t h, int n, double l, int P, const double *lp,
+                    const double *const *Ls, const double *const *dLdls, double *out);
+/* approx_Lz (models/cubic_interpolated_gp.hpp:38-73): value v(l) z and partial dv/dl z */
+GPB200_API int gpb200_approx_Lz(gpb200_handle_t h, int n, double l, int P, const double *lp,
+                     const double *const *Ls, const double *const *dLdls, const double *z,
+                     double *vz, double *dvdl_z);
+
+/* ---- a10: conditioning --------------------------------------------------------------------- */
+/* mu = Ks (K + noise_var I)^-1 y ; cov = Kss - Ks (K + noise_var I)^-1 Ks^T + jitter I
+ * (pendulum_fit.R:242-251; R/ode_gp.R:27-31; gp_derivs.py:97-113).  K n x n symmetric,
+ * Ks m x n, Kss m x m; mu length m, cov m x m.  Cholesky-based. */
+GPB200_API int gpb200_gp_condition(gpb200_handle_t h, int n, int m, const double *K, int ldk,
+                        const double *Ks, int ldks, const double *Kss, int ldkss, const double *y,
+                        double noise_var, double jitter, double *mu, double *cov, int ldcov);
+
+/* condMVN(mean, sigma, dependent = [nd..], given = [..], X.given) (R/ode_gp_library.R:17,32) for
+ * the block layout the reference uses: sigma is (ng+nd)^2 with the GIVEN block first. */
+GPB200_API int gpb200_cond_mvn(gpb200_handle_t h, int ng, int nd, const double *mean, const double *sigma,
+                    int lds, const double *x_given, double *cond_mean, double *cond_var, int ldv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H */

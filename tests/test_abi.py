@@ -1,0 +1,58 @@
+"""CPU tests of the drop-in boundary: libgpb200.so loads and exports every symbol that
+include/gpb200.h declares, the ctypes table mirrors the header, and -- with no GPU -- the library
+fails loudly instead of falling back to a CPU path."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "gpb200.h")).read()
+    return sorted(set(re.findall(r"GPB200_API[^;(]*?\b(gpb200_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gp_b200 import capi
+    lib = capi.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(capi.SIGNATURES) == syms
+    out = subprocess.check_output(["nm", "-D", "--defined-only", capi.LIB_PATH], text=True)
+    exported = sorted(set(re.findall(r" T (gpb200_\w+)", out)))
+    assert exported == syms
+    assert lib.gpb200_version() == 100
+
+
+def test_sass_is_sm100a_dmma():
+    """The built library contains sm_100a code whose O(N^3) kernels use the FP64 tensor path
+    (SASS DMMA) and cp.async (LDGSTS) -- and no other architecture."""
+    from gp_b200 import capi
+    out = subprocess.check_output(["cuobjdump", "-lelf", capi.LIB_PATH], text=True)
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    sass = subprocess.check_output(["cuobjdump", "-sass", "-fun", "_ZN3gpb16gemm_tile_kernelILb0ELb0ELi0EEEvNS_10GemmParamsE",
+                                    capi.LIB_PATH], text=True)
+    assert sass.count("DMMA.8x8x4") >= 128 and "LDGSTS" in sass
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gp_b200 import capi
+    with pytest.raises(capi.GpB200Error):
+        capi.Handle(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no CPU oracle", ""), os.path.join(dirpath, f)

@@ -1,0 +1,143 @@
+"""CPU tests of the oracle itself (runs everywhere, no GPU):
+  * the NumPy restatement against the golden vectors produced by the reference's OWN gp_derivs.py
+    (tests/golden/make_golden.py) -- the only reference-generated numbers that exist for this path;
+  * NumPy <-> plain-C <-> mpmath (50 digits) cross-checks for the Stan-Math rows, which the reference
+    does not pin ("parity unpinned");
+  * analytic gradient vs central finite differences; forward-mode Cholesky tangent vs the literal
+    dual-number LLT of covariance.cpp:13-29; Hermite end-point identities (cubic_spline_test.R)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as c
+from oracle import gp_oracle as o
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("name", ["QQ", "QR", "RQ", "RR", "QT", "TQ", "RT", "TR", "TT"])
+def test_oracle_kernels_match_reference_golden(golden, name):
+    ts, tts, l, a = golden["ts"], golden["tts"], float(golden["l"]), float(golden["a"])
+    assert relerr(a * a * o.outer_kernel(name, tts, ts, l), golden["kern_" + name]) < 1e-14
+    assert relerr(c.outer_kernel(name, tts, ts, l, a * a), golden["kern_" + name]) < 1e-14
+
+
+def test_oracle_conditioning_matches_reference_golden(golden):
+    s = float(golden["s"])
+    mu, cov = o.gp_condition(golden["K"], golden["KsK"], golden["KsKs"], golden["y"], s * s, 0.0)
+    assert relerr(mu, golden["mu_d"]) < 1e-12 and relerr(cov, golden["cov_d"]) < 1e-12
+    mu, cov = o.gp_condition(golden["K"], golden["KsKi"], golden["KsKsi"], golden["y"], s * s, 0.0)
+    assert relerr(mu, golden["mu_i"]) < 1e-12 and relerr(cov, golden["cov_i"]) < 1e-12
+    # known closed-form spot values quoted in SURVEY 8c: TT(0,0) = 3, RR(0,0.5) = 0.66187...
+    assert o.dk_TT(0.0, 0.0, 1.0) == 3.0
+    assert abs(o.dk_RR(0.0, 0.5, 1.0) - 0.75 * np.exp(-0.125)) < 1e-15
+
+
+def test_numpy_c_mpmath_agree_on_lml_and_gradient():
+    from oracle import gp_oracle_mp as m
+    rng = np.random.default_rng(1)
+    x = np.linspace(0, 10, 48)
+    y = np.sin(x) + 0.2 * rng.standard_normal(48)
+    for th in ([1.1, 0.8, 0.3], [0.6, 1.7, 0.15]):
+        v, g = o.lml_grad(x, y, *th)
+        v2, g2, info = c.lml_grad(x, y, th)
+        v3, g3 = m.lml_grad(x, y, *th)
+        assert info == 0
+        assert abs(v - v3) < 1e-11 * abs(v3) and abs(v2 - v3) < 1e-11 * abs(v3)
+        assert relerr(g, g3) < 1e-10 and relerr(g2, g3) < 1e-10
+
+
+def test_gradient_matches_finite_differences():
+    x, y = o.synth_xy(100, 3)
+    th = np.array([1.0, 1.0, 0.3])
+    _, g = o.lml_grad(x, y, *th)
+    for k in range(3):
+        tp, tm = th.copy(), th.copy()
+        tp[k] += 1e-6; tm[k] -= 1e-6
+        fd = (o.lml(x, y, *tp) - o.lml(x, y, *tm)) / 2e-6
+        assert abs(fd - g[k]) < 1e-6 * max(1, abs(g[k]))
+
+
+def test_c_oracle_matches_numpy_at_moderate_n():
+    x, y = o.synth_xy(300, 5)
+    th = o.synth_theta(4, 9)
+    out = c.lml_grad_draws(x, y, th, nthreads=2)
+    for b in range(4):
+        v, g = o.lml_grad(x, y, *th[b])
+        assert abs(out[b, 0] - v) < 1e-10 * abs(v)
+        assert relerr(out[b, 1:4], g) < 1e-9
+        assert out[b, 4] == 0
+    K = o.gram_se(x, 1.0, 1.0, 0.09)
+    assert relerr(c.cov_exp_quad(x, 1.0, 1.0) + 0.09 * np.eye(300), K) < 1e-15
+    L, info = c.llt(K)
+    assert info == 0 and relerr(L, o.cholesky_decompose(K)) < 1e-11
+
+
+def test_cholesky_semantics():
+    K = o.gram_se(np.linspace(0, 1, 20), 1.0, 0.5, 1e-3)
+    L = o.cholesky_decompose(K)
+    assert np.all(np.triu(L, 1) == 0)
+    Kbad = K.copy(); Kbad[3, 7] += 1e-6
+    with pytest.raises(o.NotPositiveDefinite):
+        o.cholesky_decompose(Kbad)          # symmetry check (abs tol 1e-8)
+    Kneg = K.copy(); Kneg[10, 10] = -1.0
+    with pytest.raises(o.NotPositiveDefinite) as ei:
+        o.cholesky_decompose(Kneg)
+    assert ei.value.info == 11
+    _, info = c.llt(Kneg)
+    assert info == 11
+    # cov_exp_quad puts alpha^2 exactly on the diagonal
+    assert np.all(np.diag(o.cov_exp_quad(np.linspace(0, 3, 9), 1.7, 0.3)) == 1.7 * 1.7)
+
+
+def test_rbf_cov_chol_closed_form_vs_literal_duals():
+    xs = np.arange(14) * 0.8
+    L, dL = o.rbf_cov_chol(xs, 0.5)
+    L2, dL2 = o.rbf_cov_chol_dual(xs, 0.5)
+    L3, dL3, info = c.rbf_cov_chol(xs, 0.5)
+    assert info == 0
+    assert relerr(L, L2) < 1e-12 and relerr(dL, dL2) < 1e-10
+    assert relerr(L3, L2) < 1e-13 and relerr(dL3, dL2) < 1e-12
+    h = 1e-6
+    Lp, _ = o.rbf_cov_chol(xs, 0.5 + h); Lm, _ = o.rbf_cov_chol(xs, 0.5 - h)
+    assert relerr((Lp - Lm) / (2 * h), dL) < 1e-6
+
+
+def test_hermite_identities_cubic_spline_test_constants():
+    # cubic_spline_test.R:4-18 : y1=5, y2=2, k1=-5, k2=3, x1=1, x2=1.75
+    y1, y2, k1, k2, x1, x2 = 5.0, 2.0, -5.0, 3.0, 1.0, 1.75
+    lp = [x1, x2]
+    Ls = [np.array([[y1]]), np.array([[y2]])]
+    dLs = [np.array([[k1]]), np.array([[k2]])]
+    assert o.approx_L(x1, lp, Ls, dLs)[0, 0] == y1
+    assert abs(o.approx_L(x2, lp, Ls, dLs)[0, 0] - y2) < 1e-15
+    z = np.array([1.0])
+    h = 1e-6
+    for x, k in ((x1, k1), (x2, k2)):
+        _, d = o.approx_Lz(x, lp, Ls, dLs, z)
+        assert abs(d[0] - k) < 1e-12
+    v1, d1 = o.approx_Lz(1.3, lp, Ls, dLs, z)
+    vp, _ = o.approx_Lz(1.3 + h, lp, Ls, dLs, z); vm, _ = o.approx_Lz(1.3 - h, lp, Ls, dLs, z)
+    assert abs((vp[0] - vm[0]) / (2 * h) - d1[0]) < 1e-7
+
+
+def test_condmvn_and_p_dotXn_consistency():
+    tn = np.arange(-2, 2.0001, 0.2)
+    Xn = np.exp(tn)
+    # with alpha = 1 the R/kernels.R quirk vanishes and the two API generations agree up to the 1e-6 jitter
+    cm, cv = o.p_dotXn(tn, Xn, (1.0, 0.9), 0.1)
+    mn, Kn = o.p_dotXn_solve(tn, Xn, (1.0, 0.9), 0.1)
+    assert relerr(cm, mn) < 1e-3
+    assert cm.shape == (len(tn),) and cv.shape == (len(tn), len(tn))
+    assert relerr(o.rk_RR(tn, tn, (1.0, 0.9), True), o.rk_RR(tn, tn, (1.0, 0.9), False)) == 0.0
+    assert relerr(o.rk_RR(tn, tn, (1.5, 0.9), True), o.rk_RR(tn, tn, (1.5, 0.9), False)) > 1e-3
+
+
+def test_lp_matches_lml_plus_priors():
+    x, y = o.synth_xy(50, 1)
+    lp = o.lp_fit_hyperparameters(x, y, np.log(0.9), np.log(1.2), np.log(0.3))
+    base = o.lml(x, y, 1.2, 0.9, 0.3, drop_constants=True)
+    extra = 3 * np.log(0.9) - 4 * 0.9 - 0.5 * 1.2 ** 2 - 0.5 * 0.3 ** 2 + np.log(0.9) + np.log(1.2) + np.log(0.3)
+    assert abs(lp - (base + extra)) < 1e-12
