@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GP hot path on B200.
+
+Metric (BASELINE.json): LML + gradient evaluations per second at N = 4096.
+A "step" is one pass of the fused path (Gram -> Cholesky -> inverse -> LML + gradient) over one
+batch of B = 256 independent hyper-parameter draws per GPU on synthetic inputs (SURVEY 8d
+"Headline"); draws are sharded over GPUs with no data-path collective (weak scaling).
+
+  value     evaluations/s with inputs resident in HBM, timed with CUDA events on the launching
+            stream, max over ranks
+  e2e       the same metric through the C ABI with HOST buffers (pinned), H2D/D2H inside the timer
+  roofline  the dominant kernel (DMMA tile GEMM): algorithmic FP64 flops / event-timed duration vs
+            the measured DMMA peak (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has no FP64)
+  cpu_baseline  the CPU oracle (LAPACK route, all host cores) on a bounded sample, rank 0, N=1 only
+
+`--impl reference` times the reference's CPU path instead: the reference itself (R + Stan Math +
+Eigen) cannot be built or run in this image, so this is the oracle port (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N = 4096
+DRAWS_PER_GPU = 256
+METRIC = "lml_grad_evals_per_sec_n4096"
+UNIT = "evals/s"
+TILE = 128
+
+
+def fp64_peak():
+    """Measured FP64 tensor (DMMA) peak of this pool's B200 in TFLOP/s, and where it came from."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        if "fp64_tflops" in mp:
+            return float(mp["fp64_tflops"]), "MEASURED_PEAKS.json fp64_tflops"
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")) as f:
+            return float(json.load(f)["fp64_dmma_tflops"]), "profiles/fp64_peak_r01.json (DMMA issue-rate microbenchmark, round 1)"
+    except Exception:
+        return 37.0, "fallback 37.0 (148 SM x 1.965 GHz x 128 flop/clk)"
+
+
+def gemm_algorithmic_flops(n):
+    """Algorithmic flops of one LML+grad evaluation that are carried by the DMMA GEMM launches:
+    N^3 (N^3/3 POTRF + 2N^3/3 inverse) minus what the 128-wide panel kernels do
+    (POTRF tiles nt*T^3/3, TRSM tiles nt(nt-1)/2*T^3, tile inverses nt*T^3/3)."""
+    nt = (n + TILE - 1) // TILE
+    t3 = float(TILE) ** 3
+    return float(n) ** 3 - t3 * (nt / 3.0 + nt * (nt - 1) / 2.0 + nt / 3.0)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.sm = []
+        self.reasons = set()
+        self.sm_max = None
+        self.ok = False
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            dev = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            while not self.stop_flag.is_set():
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(dev, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(dev)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(dev)
+                for bit, name in list(self.BAD.items()) + list(self.NOTE.items()):
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # pragma: no cover
+            self.error = repr(e)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2.0)
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def synth_inputs(rank):
+    """Synthetic workload of SURVEY 8d: x = sort(U(0, 0.05 N)), y = sin(x) + 0.5 sin(3.1 x) + 0.3 eps;
+    theta draws alpha ~ |N(0,1)| + 0.1, rho ~ Gamma(4,4) (fit_hyperparameters.stan:27), sigma ~ U(.1,.5)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    x = np.sort(rng.uniform(0.0, 0.05 * N, size=N))
+    y = np.sin(x) + 0.5 * np.sin(3.1 * x) + 0.3 * rng.standard_normal(N)
+    r2 = np.random.default_rng(1000 + rank)
+    theta = np.stack([np.abs(r2.standard_normal(DRAWS_PER_GPU)) + 0.1, r2.gamma(4.0, 0.25, DRAWS_PER_GPU),
+                      r2.uniform(0.1, 0.5, DRAWS_PER_GPU)], axis=1)
+    return x, y, theta
+
+
+def cpu_reference_evals_per_sec(n_evals, threads):
+    """Times the CPU oracle (LAPACK route) on `n_evals` draws of the N=4096 workload."""
+    from oracle import gp_oracle as o
+    x, y, theta = synth_inputs(0)
+    t0 = time.perf_counter()
+    out = []
+    for b in range(n_evals):
+        out.append(o.lml_grad_lapack(x, y, *theta[b]))
+    dt = time.perf_counter() - t0
+    return n_evals / dt, dt, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    per_step = 2
+    for _ in range(args.warmup):
+        cpu_reference_evals_per_sec(1, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_evals_per_sec(per_step, threads)
+    dt = time.perf_counter() - t0
+    v = args.steps * per_step / dt
+    sample = "%d LML+grad evaluations per step at N=%d (oracle.lml_grad_lapack: OpenBLAS dpotrf+dpotri, %d threads)" % (
+        per_step, N, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "lml+grad, 1-D SE kernel, N=4096, independent theta draws (CPU sample of %d draws/step)" % per_step,
+                       "n": N, "draws_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference (R + Stan Math + Eigen) cannot be built here; this is the CPU oracle port"}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpb200", choices=["gpb200", "reference"])
+    ap.add_argument("--draws", type=int, default=DRAWS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gp_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.draws
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    h = capi.Handle(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    h.set_stream(stream.cuda_stream)
+
+    x, y, theta = synth_inputs(rank)
+    dx = torch.from_numpy(x).to(dev)
+    dy = torch.from_numpy(y).to(dev)
+    dth = torch.from_numpy(theta).to(dev)
+    dlml = torch.empty(B, dtype=torch.float64, device=dev)
+    dgrad = torch.empty(B, 3, dtype=torch.float64, device=dev)
+    dinfo = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: HBM-resident inputs, device-pointer mode --------------------------
+    h.set_pointer_mode(True)
+
+    def step_device():
+        h.lml_grad_batched_device(N, B, dx, 0, dy, 0, dth, 0.0, True, dlml, dgrad, dinfo)
+
+    for _ in range(W):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    h.set_profiling(True)
+    launches0 = h.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = h.launch_count() - launches0
+    prof = h.get_profile()
+    h.set_profiling(False)
+    clocks = sampler.result()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max * 1e-3)
+    assert int(dinfo.abs().sum().item()) == 0, "a synthetic draw was not positive definite"
+    lml_dev = dlml.cpu().numpy().copy()
+
+    # ---------------- e2e: host (pinned) buffers through the C ABI ----------------------------
+    h.set_pointer_mode(False)
+    hx = torch.from_numpy(x).pin_memory()
+    hy = torch.from_numpy(y).pin_memory()
+    hth = torch.from_numpy(theta).pin_memory()
+    hlml = torch.empty(B, dtype=torch.float64).pin_memory()
+    hgrad = torch.empty(B, 3, dtype=torch.float64).pin_memory()
+    hinfo = torch.zeros(B, dtype=torch.int32).pin_memory()
+
+    def step_host():
+        rc = h.lib.gpb200_lml_grad_batched(h._h, N, B, hx.data_ptr(), 0, hy.data_ptr(), 0, hth.data_ptr(), 0.0, 1,
+                                           hlml.data_ptr(), hgrad.data_ptr(), hinfo.data_ptr())
+        if rc != 0:
+            raise RuntimeError("lml_grad_batched failed: %d" % rc)
+
+    step_host()
+    barrier()
+    e2 = torch.cuda.Event(enable_timing=True)
+    e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_host()
+    e3.record(stream)
+    torch.cuda.synchronize(dev)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2.elapsed_time(e3), wall_ms)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(t.item()) * 1e-3)
+    h2d = (x.nbytes + y.nbytes + theta.nbytes)
+    d2h = B * 8 + B * 24 + B * 4
+    assert np.allclose(hlml.numpy(), lml_dev, rtol=1e-12, atol=0)
+
+    # ---------------- roofline of the dominant kernel -------------------------------------------
+    peak, peak_src = fp64_peak()
+    gemm_ms, gemm_count = prof["gemm"]
+    gemm_flops_step = gemm_algorithmic_flops(N) * B
+    achieved = gemm_flops_step * K / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("gemm_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "gpb::gemm_tile_kernel (DMMA.8x8x4 FP64 tile GEMM, all launches of the step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "peak_source": peak_src + " -- of measured",
+                "launches_per_step": gemm_count // max(K, 1), "kernel_ms_per_step": gemm_ms / K,
+                "kernel_share_of_step": gemm_ms / ms if ms > 0 else None,
+                "whole_step_tflops": value / world * float(N) ** 3 * 1e-12,
+                "whole_step_frac": value / world * float(N) ** 3 * 1e-12 / peak,
+                "other_kernels_ms_per_step": {k: v[0] / K for k, v in prof.items() if k != "gemm"}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "lml+grad (Gram->Cholesky->inverse->fused trace), 1-D SE kernel, N=4096, %d independent "
+                                   "theta draws per GPU per step (SURVEY 8d headline)" % B,
+                       "n": N, "draws_per_gpu": B, "parallelism": "draws sharded over %d GPU(s), no collective" % world,
+                       "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * 2 * N * N * 8 / 1e9)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_evals = 4
+        v, dt, out = cpu_reference_evals_per_sec(n_evals, threads)
+        # the timed GPU results must equal the oracle's on the same draws (1e-9 relative)
+        for b in range(n_evals):
+            assert abs(out[b][0] - lml_dev[b]) <= 1e-9 * abs(out[b][0]), (b, out[b][0], lml_dev[b])
+            g = hgrad.numpy()[b]
+            assert np.max(np.abs(g - out[b][1])) <= 1e-9 * np.max(np.abs(out[b][1])), (b, g, out[b][1])
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d of the %d draws of one step at N=%d, oracle.lml_grad_lapack (OpenBLAS "
+                                          "dpotrf+dpotri, %d threads), %.1f s; GPU results checked against them to 1e-9" % (
+                                              n_evals, B, N, threads, dt)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    h.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

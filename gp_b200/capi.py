@@ -33,6 +33,8 @@ SIGNATURES = {
     "gpb200_launch_count": (_ll, [_h]),
     "gpb200_version": (C.c_int, []),
     "gpb200_set_workspace_limit": (C.c_int, [_h, _ll]),
+    "gpb200_set_profiling": (C.c_int, [_h, C.c_int]),
+    "gpb200_get_profile": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
     "gpb200_kernel_eval": (C.c_int, [_h, C.c_int, _ll, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     "gpb200_gram_outer": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                     C.c_void_p, C.c_int]),
@@ -153,6 +155,16 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self.lib.gpb200_launch_count(self._h))
+
+    PROFILE_CLASSES = ("gemm", "potrf_tile", "trsm_tile", "gram", "solve", "other")
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.gpb200_set_profiling(self._h, int(bool(on))), "set_profiling")
+
+    def get_profile(self):
+        ms = np.zeros(6); cnt = np.zeros(6, dtype=np.int64)
+        self._check(self.lib.gpb200_get_profile(self._h, _ptr(ms), _ptr(cnt)), "get_profile")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 
     # -- a9 -------------------------------------------------------------------------------------
     def kernel_eval(self, kind, tj, tk, l, amp2=1.0):

@@ -241,6 +241,7 @@ __global__ void extract_diag_kernel(int np, const double *__restrict__ L, long l
 
 int extract_diag(Handle *h, int np, const double *L, long long stride, double *dvec, int batch) {
   dim3 grid((np + 255) / 256, batch);
+  ProfScope ps__(h, PC_OTHER);
   extract_diag_kernel<<<grid, 256, 0, h->stream>>>(np, L, stride, dvec);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -352,6 +353,32 @@ extern "C" long long gpb200_launch_count(gpb200_handle_t h) { return h ? h->laun
 extern "C" int gpb200_set_workspace_limit(gpb200_handle_t h, long long bytes) {
   if (!h) return -1;
   h->ws_limit = bytes;
+  return 0;
+}
+
+extern "C" int gpb200_set_profiling(gpb200_handle_t h, int on) {
+  if (!h) return -1;
+  h->profiling = on ? 1 : 0;
+  h->prof.clear();
+  h->ev_used = 0;
+  return 0;
+}
+
+// Sums the event-bracketed launch durations per kernel class since profiling was switched on (or
+// since the last call), then resets.  ms_out / count_out: arrays of 6 (gemm, potrf tile, trsm tile,
+// gram, solves, other).  Synchronises the stream.
+extern "C" int gpb200_get_profile(gpb200_handle_t h, double *ms_out, long long *count_out) {
+  CHECK_H(h);
+  GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < PC_COUNT; c++) { ms_out[c] = 0.0; count_out[c] = 0; }
+  for (const auto &r : h->prof) {
+    float ms = 0.f;
+    GPB_CUDA(h, cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_out[r.cls] += ms;
+    count_out[r.cls]++;
+  }
+  h->prof.clear();
+  h->ev_used = 0;
   return 0;
 }
 
@@ -996,6 +1023,7 @@ extern "C" int gpb200_cond_mvn(gpb200_handle_t h, int ng, int nd, const double *
     dcm = a.take<double>(nd); dcv = a.take<double>((size_t)nd * nd); ldo = nd;
   }
   double *rhs = a.take<double>(ng);
+  ProfScope ps__(h, PC_OTHER);
   sub_kernel<<<(ng + 255) / 256, 256, 0, h->stream>>>(ng, dxg, dmean, rhs);
   GPB_LAUNCH_CHECK(h);
   int hinfo = 0;

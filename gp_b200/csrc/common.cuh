@@ -55,9 +55,42 @@ struct Handle {
   size_t ws_bytes = 0;
   // cached device-side task lists keyed by (kind, nt)
   std::map<long long, std::pair<TileTask *, std::vector<int>>> task_cache;
-  // pinned staging for small host<->device scalars
-  double *pinned = nullptr;
-  size_t pinned_bytes = 0;
+  // optional per-kernel-class timing with CUDA events on the handle's stream (bench.py roofline)
+  int profiling = 0;
+  struct ProfRec { int cls; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  cudaEvent_t prof_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  }
+};
+
+enum ProfClass { PC_GEMM = 0, PC_POTRF = 1, PC_TRSM = 2, PC_GRAM = 3, PC_SOLVE = 4, PC_OTHER = 5, PC_COUNT = 6 };
+
+// brackets one kernel launch with events when profiling is on
+struct ProfScope {
+  Handle *h;
+  cudaEvent_t e0 = nullptr;
+  int cls;
+  ProfScope(Handle *h_, int cls_) : h(h_), cls(cls_) {
+    if (h->profiling) {
+      e0 = h->prof_event();
+      cudaEventRecord(e0, h->stream);
+    }
+  }
+  ~ProfScope() {
+    if (h->profiling) {
+      cudaEvent_t e1 = h->prof_event();
+      cudaEventRecord(e1, h->stream);
+      h->prof.push_back({cls, e0, e1});
+    }
+  }
 };
 
 #define GPB_CUDA(h, call)                                                                     \

@@ -246,6 +246,7 @@ static int launch_one(Handle *h, const GemmParams &p, int ntasks, int batch) {
     configured = true;
   }
   dim3 grid(ntasks, batch);
+  ProfScope ps__(h, PC_GEMM);
   kern<<<grid, NTHREADS, GEMM_SMEM_BYTES, h->stream>>>(p);
   GPB_LAUNCH_CHECK(h);
   return 0;

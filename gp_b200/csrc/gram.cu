@@ -191,6 +191,7 @@ int launch_kernel_eval(Handle *h, int kind, long long len, const double *tj, con
                        double l, double *out) {
   if (len <= 0) return 0;
   const int blocks = (int)((len + 255) / 256 > 148 * 16 ? 148 * 16 : (len + 255) / 256);
+  ProfScope ps__(h, PC_GRAM);
   kernel_eval_kernel<<<blocks, 256, 0, h->stream>>>(kind, len, tj, tk, amp2, l, out);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -200,6 +201,7 @@ int launch_gram_outer(Handle *h, int kind, int n, int m, const double *x, const 
                       double *K, long long ldk) {
   if (n <= 0 || m <= 0) return 0;
   dim3 grid((n + TILE - 1) / TILE, (m + TILE - 1) / TILE);
+  ProfScope ps__(h, PC_GRAM);
   gram_outer_kernel<<<grid, 256, 0, h->stream>>>(kind, n, m, x, y, amp2, l, K, ldk);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -209,6 +211,7 @@ int launch_gram_se_batched(Handle *h, int n, int np, const double *x, long long 
                            double jitter, int lower_only, double *K, long long stride, int batch) {
   const int nt = np / TILE;
   dim3 grid(nt * nt, batch);
+  ProfScope ps__(h, PC_GRAM);
   gram_se_batched_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, x_stride, theta, jitter, lower_only, K, stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -217,6 +220,7 @@ int launch_gram_se_batched(Handle *h, int n, int np, const double *x, long long 
 int launch_gram_rbf_tangent(Handle *h, int n, int np, const double *x, double l, double jitter, double *S,
                             double *Sdot) {
   dim3 grid(np / TILE, np / TILE);
+  ProfScope ps__(h, PC_GRAM);
   gram_rbf_tangent_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, l, jitter, S, Sdot);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -226,6 +230,7 @@ int launch_gram_deriv(Handle *h, int n, int nblocks, const double *t, double alp
                       double jitter, int quirk, double *K, long long ldk) {
   const int N = n * nblocks;
   dim3 grid((N + TILE - 1) / TILE, (N + TILE - 1) / TILE);
+  ProfScope ps__(h, PC_GRAM);
   gram_deriv_kernel<<<grid, 256, 0, h->stream>>>(n, nblocks, t, alpha, rho, noise[0], nblocks > 1 ? noise[1] : 0.0,
                                                 nblocks > 2 ? noise[2] : 0.0, jitter, quirk, K, ldk);
   GPB_LAUNCH_CHECK(h);
@@ -236,6 +241,7 @@ int launch_gram_ard(Handle *h, int n, int m, int D, const double *X, long long l
                     double alpha, const double *rho, int rho_len, double *K, long long ldk) {
   if (n <= 0 || m <= 0) return 0;
   dim3 grid((n + 127) / 128, (m + 63) / 64);
+  ProfScope ps__(h, PC_GRAM);
   gram_ard_kernel<<<grid, 256, 0, h->stream>>>(n, m, D, X, ldx, Y, ldy, alpha, rho, rho_len, K, ldk);
   GPB_LAUNCH_CHECK(h);
   return 0;

@@ -221,6 +221,7 @@ int panel_smem_setup(Handle *h) {
 }
 
 int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n, int batch, int *info) {
+  ProfScope ps__(h, PC_POTRF);
   potrf_tile_kernel<<<batch, 256, 0, h->stream>>>(L, ld, stride, tile_idx, n, info);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -229,6 +230,7 @@ int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int 
 int launch_trsm_tiles(Handle *h, double *L, long long ld, long long stride, int tile_col, int ntiles_below, int batch) {
   if (ntiles_below <= 0) return 0;
   dim3 grid(ntiles_below, batch);
+  ProfScope ps__(h, PC_TRSM);
   trsm_tile_kernel<0><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, L, ld, stride, tile_col, 0);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -236,6 +238,7 @@ int launch_trsm_tiles(Handle *h, double *L, long long ld, long long stride, int 
 
 int launch_tile_inverse(Handle *h, const double *L, double *W, long long ld, long long stride, int ntiles, int batch) {
   dim3 grid(ntiles, batch);
+  ProfScope ps__(h, PC_TRSM);
   trsm_tile_kernel<1><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, W, ld, stride, 0, ntiles);
   GPB_LAUNCH_CHECK(h);
   return 0;

@@ -280,6 +280,7 @@ __global__ void hermite_kernel(long long len, int n, const double *__restrict__ 
 int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, const double *y, long long y_stride,
                         int n_valid, double *z, long long z_stride, int batch) {
   dim3 grid(np / TILE, batch);
+  ProfScope ps__(h, PC_SOLVE);
   trmv_lower_n_kernel<<<grid, 256, 0, h->stream>>>(np, W, stride, y, y_stride, n_valid, z, z_stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -288,6 +289,7 @@ int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, co
 int launch_trmv_lower_t(Handle *h, int np, const double *W, long long stride, const double *z, long long z_stride,
                         double *a, long long a_stride, int batch) {
   dim3 grid(np / 8, batch);
+  ProfScope ps__(h, PC_SOLVE);
   trmv_lower_t_kernel<<<grid, 256, 0, h->stream>>>(np, W, stride, z, z_stride, a, a_stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -305,6 +307,7 @@ int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag,
     snprintf(h->err, sizeof(h->err), "trsv_blocked: n too large for the shared-memory solution vector");
     return -3;
   }
+  ProfScope ps__(h, PC_SOLVE);
   trsv_blocked_kernel<<<batch, 256, smem, h->stream>>>(np, L, Wdiag, stride, y, y_stride, mu, n_valid, z, z_stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -312,12 +315,14 @@ int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag,
 
 int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec, const double *z, const double *a,
                     const double *partial, int ntasks, const double *theta, double *lml, double *grad, int batch) {
+  ProfScope ps__(h, PC_OTHER);
   finalize_kernel<<<batch, 256, 0, h->stream>>>(n, np, want_grad, dvec, z, a, partial, ntasks, theta, lml, grad);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
 
 int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2) {
+  ProfScope ps__(h, PC_OTHER);
   sumsq_logdiag_kernel<<<1, 256, 0, h->stream>>>(n, z, L, ldl, out2);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -326,6 +331,7 @@ int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, lon
 int launch_pack(Handle *h, int rows, int cols, const double *src, long long lds, int rp, int cp, double *dst,
                 int mode, double diag_add) {
   dim3 grid((rp + 255) / 256, cp);
+  ProfScope ps__(h, PC_OTHER);
   pack_kernel<<<grid, 256, 0, h->stream>>>(rows, cols, src, lds, rp, cp, dst, mode, diag_add);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -335,6 +341,7 @@ int launch_unpack(Handle *h, int rows, int cols, const double *src, long long ld
                   int mode, double diag_add) {
   if (rows <= 0 || cols <= 0) return 0;
   dim3 grid((rows + 255) / 256, cols);
+  ProfScope ps__(h, PC_OTHER);
   unpack_kernel<<<grid, 256, 0, h->stream>>>(rows, cols, src, lds_src, dst, ldd, mode, diag_add);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -342,6 +349,7 @@ int launch_unpack(Handle *h, int rows, int cols, const double *src, long long ld
 
 int launch_phi_lower(Handle *h, int np, double *A) {
   dim3 grid((np + 255) / 256, np);
+  ProfScope ps__(h, PC_OTHER);
   phi_lower_kernel<<<grid, 256, 0, h->stream>>>(np, A);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -349,6 +357,7 @@ int launch_phi_lower(Handle *h, int np, double *A) {
 
 int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv, const double *z, const double *add,
                   double *out) {
+  ProfScope ps__(h, PC_SOLVE);
   gemv_t_kernel<<<(cols + 7) / 8, 256, 0, h->stream>>>(rows, cols, V, ldv, z, add, out);
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -357,6 +366,7 @@ int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv,
 int launch_hermite(Handle *h, long long len, int n, const double *y1, const double *y2, const double *k1,
                    const double *k2, double x1, double x2, double l, double *v, double *dvdl) {
   const int blocks = (int)((len + 255) / 256 > 148 * 8 ? 148 * 8 : (len + 255) / 256);
+  ProfScope ps__(h, PC_OTHER);
   hermite_kernel<<<blocks, 256, 0, h->stream>>>(len, n, y1, y2, k1, k2, x1, x2, l, v, dvdl);
   GPB_LAUNCH_CHECK(h);
   return 0;

@@ -47,6 +47,12 @@ GPB200_API int gpb200_version(void);
 /* cap on the device workspace the batched entry points may allocate (bytes; 0 = 60% of free) */
 GPB200_API int gpb200_set_workspace_limit(gpb200_handle_t h, long long bytes);
 
+/* per-kernel-class timing with CUDA events on the handle's stream (used by bench.py for the
+ * roofline of the dominant kernel).  Classes: 0 DMMA tile GEMM, 1 POTRF tile, 2 TRSM tile,
+ * 3 Gram, 4 triangular mat-vec/solves, 5 other.  get_profile synchronises, sums and resets. */
+GPB200_API int gpb200_set_profiling(gpb200_handle_t h, int on);
+GPB200_API int gpb200_get_profile(gpb200_handle_t h, double *ms_out6, long long *count_out6);
+
 /* ---- a9: kernel functions ------------------------------------------------------------------ */
 /* kinds of derivative_kernels.R:39-73 (Q = value, R = first derivative, T = second derivative;
  * first letter goes with tj) */

@@ -454,3 +454,35 @@ def synth_theta(B, seed):
     rho = rng.gamma(4.0, 1.0 / 4.0, size=B)
     sigma = rng.uniform(0.1, 0.5, size=B)
     return np.stack([alpha, rho, sigma], axis=1)
+
+
+def lml_grad_lapack(x, y, alpha, rho, sigma, jitter=0.0):
+    """Same quantity as lml_grad with the cheapest LAPACK route (dpotrf + dpotri = N^3 flops, all
+    BLAS-3): the strongest CPU baseline this oracle can offer; used by bench.py's cpu_baseline and
+    --impl reference legs.  Checked against lml_grad in tests/test_oracle.py."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = x.shape[0]
+    d = x[:, None] - x[None, :]
+    d *= d
+    E = np.exp(d * (-0.5 / (rho * rho)))        # unit-amplitude SE kernel
+    K = (alpha * alpha) * E
+    K[np.diag_indices_from(K)] = alpha * alpha + sigma * sigma + jitter
+    L, info = sla.lapack.dpotrf(K, lower=1, clean=1, overwrite_a=1)
+    if info != 0:
+        raise NotPositiveDefinite("not positive definite", int(info))
+    z = sla.solve_triangular(L, y, lower=True, check_finite=False)
+    a = sla.solve_triangular(L, z, lower=True, trans="T", check_finite=False)
+    val = -0.5 * n * LOG_TWO_PI - np.sum(np.log(np.diag(L))) - 0.5 * float(z @ z)
+    Kinv, info = sla.lapack.dpotri(L, lower=1, overwrite_c=1)   # lower triangle of K^-1
+    il = np.tril_indices(n, -1)
+    kd = np.diag(Kinv)
+    # sum over the full symmetric matrix = diagonal + 2 * strict lower
+    M_low = a[il[0]] * a[il[1]] - Kinv[il]
+    e_low = E[il]
+    s_se = float(np.sum(a * a - kd) + 2.0 * np.sum(M_low * e_low))
+    s_d2 = float(2.0 * np.sum(M_low * e_low * d[il]))
+    g_alpha = alpha * s_se
+    g_rho = 0.5 * alpha * alpha * s_d2 / rho ** 3
+    g_sigma = sigma * float(np.sum(a * a) - np.sum(kd))
+    return float(val), np.array([g_alpha, g_rho, g_sigma])
