@@ -31,16 +31,16 @@ constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * (int)sizeof(double)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
 }
 
 template <bool A_KC, bool B_KC, int EPI>
@@ -91,48 +91,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
   const long long stepA = A_KC ? (long long)KC : (long long)KC * lda;
   const long long stepB = B_KC ? (long long)KC : (long long)KC * ldb;
 
-  auto load_stage = [&](int stage) {
+  // The source addresses are recomputed from constant bases for every chunk: incrementing the
+  // registers an in-flight LDGSTS still reads costs a long-scoreboard (WAR) stall per chunk.
+  auto load_stage = [&](int stage, int chunk) {
     double *sA = smem + stage * 2 * STAGE_DOUBLES;
     double *sB = sA + STAGE_DOUBLES;
+    const long long offA = (long long)chunk * stepA, offB = (long long)chunk * stepB;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      cp_async16(sA + dstA[r], srcA[r]);
-      srcA[r] += stepA;
-    }
+    for (int r = 0; r < 4; r++) cp_async16(sA + dstA[r], srcA[r] + offA);
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      cp_async16(sB + dstB[r], srcB[r]);
-      srcB[r] += stepB;
-    }
+    for (int r = 0; r < 4; r++) cp_async16(sB + dstB[r], srcB[r] + offB);
+  };
+  auto load_frags = [&](const double *sA, const double *sB, int kk, double (&af)[8], double (&bf)[4]) {
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+      af[mi] = A_KC ? sA[(wm + mi * 8 + g) * LD_KC + kk * 4 + t] : sA[(kk * 4 + t) * LD_MC + wm + mi * 8 + g];
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+      bf[ni] = B_KC ? sB[(wn + ni * 8 + g) * LD_KC + kk * 4 + t] : sB[(kk * 4 + t) * LD_MC + wn + ni * 8 + g];
   };
 
+  // prologue: all STAGES stages in flight, wait for chunk 0, first fragments in registers
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) {
-    if (s < nk) load_stage(s);
+  for (int s = 0; s < STAGES; s++) {
+    if (s < nk) load_stage(s, s);
     cp_async_commit();
   }
+  cp_async_wait<STAGES - 1>();
+  __syncthreads();
+  double af[2][8], bf[2][4];
+  load_frags(smem, smem + STAGE_DOUBLES, 0, af[0], bf[0]);
 
   for (int kc = 0; kc < nk; kc++) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    if (kc + STAGES - 1 < nk) load_stage((kc + STAGES - 1) % STAGES);
-    cp_async_commit();
-
     const double *sA = smem + (kc % STAGES) * 2 * STAGE_DOUBLES;
     const double *sB = sA + STAGE_DOUBLES;
 #pragma unroll
     for (int kk = 0; kk < KC / 4; kk++) {
-      double af[8], bf[4];
-#pragma unroll
-      for (int mi = 0; mi < 8; mi++)
-        af[mi] = A_KC ? sA[(wm + mi * 8 + g) * LD_KC + kk * 4 + t] : sA[(kk * 4 + t) * LD_MC + wm + mi * 8 + g];
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk < KC / 4 - 1) {
+        load_frags(sA, sB, kk + 1, af[nxt], bf[nxt]);
+      } else {
+        // Chunk transition, hidden behind the DMMAs of this last k-step: everybody has finished
+        // reading stage kc (its last fragments are in registers), chunk kc+1 has landed.
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kc + STAGES < nk) load_stage(kc % STAGES, kc + STAGES);
+        cp_async_commit();
+        if (kc + 1 < nk) {
+          const double *nA = smem + ((kc + 1) % STAGES) * 2 * STAGE_DOUBLES;
+          load_frags(nA, nA + STAGE_DOUBLES, 0, af[nxt], bf[nxt]);
+        }
+      }
 #pragma unroll
       for (int ni = 0; ni < 4; ni++)
-        bf[ni] = B_KC ? sB[(wn + ni * 8 + g) * LD_KC + kk * 4 + t] : sB[(kk * 4 + t) * LD_MC + wn + ni * 8 + g];
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++)
-#pragma unroll
-        for (int mi = 0; mi < 8; mi++) dmma884(acc[ni][mi], bf[ni], af[mi]);
+        for (int mi = 0; mi < 8; mi++) dmma884(acc[ni][mi], bf[cur][ni], af[cur][mi]);
     }
   }
   cp_async_wait<0>();
