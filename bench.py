@@ -125,14 +125,17 @@ def synth_inputs(rank):
 
 
 def cpu_reference_evals_per_sec(n_evals, threads):
-    """Times the CPU oracle (LAPACK route) on `n_evals` draws of the N=4096 workload."""
+    """Times the CPU oracle (LAPACK route) on `n_evals` draws of the N=4096 workload with `threads`
+    BLAS threads (torchrun exports OMP_NUM_THREADS=1, so the pool size is set explicitly)."""
     from oracle import gp_oracle as o
+    from threadpoolctl import threadpool_limits
     x, y, theta = synth_inputs(0)
-    t0 = time.perf_counter()
     out = []
-    for b in range(n_evals):
-        out.append(o.lml_grad_lapack(x, y, *theta[b]))
-    dt = time.perf_counter() - t0
+    with threadpool_limits(limits=threads):
+        t0 = time.perf_counter()
+        for b in range(n_evals):
+            out.append(o.lml_grad_lapack(x, y, *theta[b]))
+        dt = time.perf_counter() - t0
     return n_evals / dt, dt, out
 
 
@@ -141,6 +144,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
+    # all host threads: torchrun pins OMP_NUM_THREADS=1 for its children, undo that before NumPy loads
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(threads)
     per_step = 2
     for _ in range(args.warmup):
         cpu_reference_evals_per_sec(1, threads)

@@ -1,0 +1,79 @@
+"""Host-side mirror of R/ode_gp_library.R (and of the older R/ode_gp.R): the conditioning API.
+
+p_Xn / p_dotXn keep the reference signatures (tn, Xn, phi_n, sigma_n) and return what
+condMVNorm::condMVN returns, {"condMean", "condVar"} (R/ode_gp_library.R:17,32).  UU/UD/DD, which
+the reference never defines, are QQ/QR/RR of R/kernels.R as R/ode_gp.R:5-8,23-26 shows
+(SURVEY Appendix A.2).  p_dotXn_mnKn is the R/ode_gp.R:19-32 variant returning {"mn", "Kn"}.
+sample_derivs is pendulum_fit.R:227-255.  The joint matrix is assembled by one Gram kernel and
+conditioned by the tiled Cholesky; nothing is computed on the host.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+
+def condMVN(mean, sigma, dependent_ind, given_ind, X_given, handle=None):
+    """condMVNorm::condMVN for the layout the reference uses: given indices 0..ng-1 first, dependent
+    indices ng..N-1 after (R/ode_gp_library.R:17: condMVN(m, K, (N+1):(2*N), 1:N, Xn))."""
+    ng = len(given_ind)
+    N = np.asarray(sigma).shape[0]
+    if list(given_ind) != list(range(ng)) or list(dependent_ind) != list(range(ng, N)):
+        raise capi.GpB200Error("condMVN: only the reference's block layout (given block first) is supported")
+    cm, cv = (handle or capi.default_handle()).cond_mvn(mean, sigma, ng, X_given)
+    return {"condMean": cm, "condVar": cv}
+
+
+def p_dotXn(tn, Xn, phi_n, sigma_n, quirk=True, handle=None):  # R/ode_gp_library.R:23-33
+    h = handle or capi.default_handle()
+    tn = np.asarray(tn, dtype=np.float64)
+    n = tn.shape[0]
+    K = h.gram_deriv(tn, float(phi_n[0]), float(phi_n[1]), [float(sigma_n), 0.0], 1e-6, nblocks=2, quirk=quirk)
+    cm, cv = h.cond_mvn(np.zeros(2 * n), K, n, Xn)
+    return {"condMean": cm, "condVar": cv}
+
+
+def p_Xn(tn, Xn, phi_n, sigma_n, handle=None):  # R/ode_gp_library.R:3-18
+    h = handle or capi.default_handle()
+    tn = np.asarray(tn, dtype=np.float64)
+    n = tn.shape[0]
+    UU = h.gram_outer("QQ", tn, tn, float(phi_n[1]), float(phi_n[0]) ** 2)
+    K = np.empty((2 * n, 2 * n), order="F")
+    K[:n, :n] = UU + float(sigma_n) ** 2 * np.eye(n)
+    K[:n, n:] = UU.T
+    K[n:, :n] = UU.T
+    K[n:, n:] = UU
+    K[np.diag_indices(2 * n)] += 1e-6
+    cm, cv = h.cond_mvn(np.zeros(2 * n), K, n, Xn)
+    return {"condMean": cm, "condVar": cv}
+
+
+def p_dotXn_mnKn(tn, Xn, phi_n, sigma_n, quirk=True, handle=None):  # R/ode_gp.R:19-32
+    h = handle or capi.default_handle()
+    a2, l = float(phi_n[0]) ** 2, float(phi_n[1])
+    QQ = h.gram_outer("QQ", tn, tn, l, a2)
+    RQ = h.gram_outer("QR", tn, tn, l, a2).T
+    RR = h.gram_outer("RR_QUIRK" if quirk else "RR", tn, tn, l, a2)
+    mn, Kn = h.gp_condition(QQ, RQ, RR, Xn, float(sigma_n) ** 2, 0.0)
+    return {"mn": mn, "Kn": Kn}
+
+
+def sample_derivs_moments(params, ynoise, ti, handle=None):
+    """pendulum_fit.R:227-251: params = (l, a, sy); returns build_mu / build_cov."""
+    h = handle or capi.default_handle()
+    l, a, sy = (float(v) for v in params)
+    K = h.gram_outer("QQ", ti, ti, l, a * a)
+    KsK = h.gram_outer("RQ", ti, ti, l, a * a)
+    KsKs = h.gram_outer("RR", ti, ti, l, a * a)
+    return h.gp_condition(K, KsK, KsKs, ynoise, sy * sy, 1e-8)
+
+
+def sample_derivs(params, ynoise, ti, rng=None, handle=None):
+    """pendulum_fit.R:227-255 including the MASS::mvrnorm(1, mu, Sigma) draw (:253): the draw is
+    mu + L z with L the GPU Cholesky factor of the posterior covariance and z ~ N(0, I) from `rng`."""
+    h = handle or capi.default_handle()
+    rng = rng or np.random.default_rng()
+    mu, cov = sample_derivs_moments(params, ynoise, ti, handle=h)
+    L = h.potrf(cov)
+    return mu + h.trmv_lower(L, rng.standard_normal(mu.shape[0]))

@@ -457,15 +457,16 @@ def synth_theta(B, seed):
 
 
 def lml_grad_lapack(x, y, alpha, rho, sigma, jitter=0.0):
-    """Same quantity as lml_grad with the cheapest LAPACK route (dpotrf + dpotri = N^3 flops, all
-    BLAS-3): the strongest CPU baseline this oracle can offer; used by bench.py's cpu_baseline and
+    """Same quantity as lml_grad by the cheapest LAPACK route (dpotrf + dpotri = N^3 flops, all
+    BLAS-3, threaded by OpenBLAS) with the trace contractions written as BLAS dot / gemv calls: the
+    strongest CPU baseline this oracle can offer; used by bench.py's cpu_baseline and
     --impl reference legs.  Checked against lml_grad in tests/test_oracle.py."""
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
     n = x.shape[0]
-    d = x[:, None] - x[None, :]
-    d *= d
-    E = np.exp(d * (-0.5 / (rho * rho)))        # unit-amplitude SE kernel
+    d2 = np.subtract.outer(x, x)
+    np.square(d2, out=d2)
+    E = np.exp(d2 * (-0.5 / (rho * rho)))       # unit-amplitude SE kernel, exact 1 on the diagonal
     K = (alpha * alpha) * E
     K[np.diag_indices_from(K)] = alpha * alpha + sigma * sigma + jitter
     L, info = sla.lapack.dpotrf(K, lower=1, clean=1, overwrite_a=1)
@@ -474,15 +475,16 @@ def lml_grad_lapack(x, y, alpha, rho, sigma, jitter=0.0):
     z = sla.solve_triangular(L, y, lower=True, check_finite=False)
     a = sla.solve_triangular(L, z, lower=True, trans="T", check_finite=False)
     val = -0.5 * n * LOG_TWO_PI - np.sum(np.log(np.diag(L))) - 0.5 * float(z @ z)
-    Kinv, info = sla.lapack.dpotri(L, lower=1, overwrite_c=1)   # lower triangle of K^-1
-    il = np.tril_indices(n, -1)
-    kd = np.diag(Kinv)
-    # sum over the full symmetric matrix = diagonal + 2 * strict lower
-    M_low = a[il[0]] * a[il[1]] - Kinv[il]
-    e_low = E[il]
-    s_se = float(np.sum(a * a - kd) + 2.0 * np.sum(M_low * e_low))
-    s_d2 = float(2.0 * np.sum(M_low * e_low * d[il]))
+    # lower triangle of K^-1; the strict upper triangle stays exactly zero (clean=1 above), so a
+    # full-matrix dot with a symmetric matrix S gives sum_{i>=j} Kinv_ij S_ij.
+    Kinv, info = sla.lapack.dpotri(L, lower=1, overwrite_c=1)
+    kd = np.diag(Kinv).copy()
+    ED2 = E * d2
+    tr_se = 2.0 * float(np.vdot(Kinv, E)) - float(np.sum(kd))          # tr(Kinv E), E_ii = 1
+    tr_d2 = 2.0 * float(np.vdot(Kinv, ED2))                            # diagonal of E*d2 is zero
+    s_se = float(a @ (E @ a)) - tr_se
+    s_d2 = float(a @ (ED2 @ a)) - tr_d2
     g_alpha = alpha * s_se
     g_rho = 0.5 * alpha * alpha * s_d2 / rho ** 3
-    g_sigma = sigma * float(np.sum(a * a) - np.sum(kd))
+    g_sigma = sigma * (float(a @ a) - float(np.sum(kd)))
     return float(val), np.array([g_alpha, g_rho, g_sigma])

@@ -1,0 +1,66 @@
+// stan/gp_lml_stan.hpp -- Stan external C++ function backed by libgpb200.so.
+//
+// NOT COMPILED IN THE BUILD CONTAINER (no Stan Math / Eigen there).  Usage mirrors the mechanism the
+// reference uses for models/cubic_interpolated_gp.hpp (test_interpolate.R:16-23):
+//
+//   functions { real gp_lml(real[] x, vector y, real alpha, real rho, real sigma); }
+//   model     { target += gp_lml(t, y, alpha, rho, sigma); ... priors ... }
+//
+//   stanc(file, allow_undefined = TRUE)
+//   stan_model(stanc_ret = ..., includes = '#include "/abs/path/stan/gp_lml_stan.hpp"')
+//   and link with  -L<repo>/gp_b200/lib -lgpb200
+//
+// It replaces lines 19-25 and 31 of models/fit_hyperparameters.stan (cov_exp_quad, diagonal add,
+// cholesky_decompose, multi_normal_cholesky) and their reverse sweep by one GPU call: the value is
+// the LML WITH constants and the three partials are injected with precomputed_gradients, the same
+// device the reference uses in cubic_interpolated_gp.hpp:28 (precomp_v_vari).
+// A non-positive-definite matrix throws std::domain_error, as Stan Math's cholesky_decompose does,
+// so NUTS rejects the proposal.
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+extern "C" {
+#include "../include/gpb200.h"
+}
+
+namespace gpb200_stan {
+inline gpb200_handle_t handle() {
+  static thread_local gpb200_handle_t h = nullptr;
+  if (!h) {
+    if (gpb200_create(&h, 0) != 0) throw std::runtime_error("gpb200: no usable B200 GPU (no CPU fallback)");
+  }
+  return h;
+}
+inline void eval(const std::vector<double>& x, const Eigen::VectorXd& y, double alpha, double rho, double sigma,
+                 double& lml, double* grad) {
+  const double theta[3] = {alpha, rho, sigma};
+  const int rc = gpb200_lml_grad(handle(), (int)x.size(), x.data(), y.data(), theta, 0.0, &lml, grad);
+  if (rc > 0) throw std::domain_error("gp_lml: covariance is not positive definite (pivot " + std::to_string(rc) + ")");
+  if (rc < 0) throw std::runtime_error(std::string("gp_lml: ") + gpb200_last_error(handle()));
+}
+}  // namespace gpb200_stan
+
+// reverse-mode overload: any of alpha, rho, sigma may be var
+template <typename T0__, typename T1__, typename T2__>
+typename boost::math::tools::promote_args<T0__, T1__, T2__>::type
+gp_lml(const std::vector<double>& x, const Eigen::Matrix<double, Eigen::Dynamic, 1>& y, const T0__& alpha,
+       const T1__& rho, const T2__& sigma, std::ostream* pstream__) {
+  using stan::math::value_of;
+  double lml, g[3];
+  gpb200_stan::eval(x, y, value_of(alpha), value_of(rho), value_of(sigma), lml, g);
+  std::vector<stan::math::var> operands;
+  std::vector<double> partials;
+  if (!stan::is_constant<T0__>::value) { operands.push_back(alpha); partials.push_back(g[0]); }
+  if (!stan::is_constant<T1__>::value) { operands.push_back(rho); partials.push_back(g[1]); }
+  if (!stan::is_constant<T2__>::value) { operands.push_back(sigma); partials.push_back(g[2]); }
+  return stan::math::precomputed_gradients(lml, operands, partials);
+}
+
+// all-double overload (generated quantities / transformed data), like cubic_interpolated_gp.hpp:34-36
+inline double gp_lml(const std::vector<double>& x, const Eigen::Matrix<double, Eigen::Dynamic, 1>& y,
+                     const double& alpha, const double& rho, const double& sigma, std::ostream* pstream__) {
+  double lml;
+  gpb200_stan::eval(x, y, alpha, rho, sigma, lml, nullptr);
+  return lml;
+}

@@ -1,0 +1,104 @@
+"""GPU tests of the host-side mirror of the reference's R-level interface (same names, argument
+order and return fields as R/kernels.R, derivative_kernels.R, R/ode_gp_library.R, R/ode_gp.R,
+covariance.cpp) -- written the way R/tests.R exercises the reference: deterministic grids
+seq(-2, 2, 0.2), exp(t) data, then numeric comparison with the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_derivative_kernels_elementwise_signatures(handle):
+    from gp_b200 import derivative_kernels as dk
+    tj = np.linspace(-1, 2, 31); tk = np.linspace(0.5, 1.5, 31)
+    for name in ("QQ", "QR", "RQ", "RR", "QT", "TQ", "RT", "TR", "TT"):
+        got = getattr(dk, name)(tj, tk, 0.8, handle=handle)
+        assert relerr(got, o.DERIV_KERNELS[name](tj, tk, 0.8)) < 1e-13
+    assert dk.TT(0.0, 0.0, 1.0, handle=handle) == 3.0          # SURVEY 8c spot value
+    assert relerr(dk.outer("RQ", tj, tk, 0.8, 2.0, handle=handle), 2.0 * o.outer_kernel("RQ", tj, tk, 0.8)) < 1e-13
+
+
+def test_r_kernels_api(handle):
+    from gp_b200 import kernels as rk
+    x = np.arange(-2, 2.0001, 0.2)
+    phi = (1.4, 0.7)
+    assert relerr(rk.QQ(x, x, phi, handle=handle), o.rk_QQ(x, x, phi)) < 1e-13
+    assert relerr(rk.QR(x, x, phi, handle=handle), o.rk_QR(x, x, phi)) < 1e-13
+    assert relerr(rk.RR(x, x, phi, handle=handle), o.rk_RR(x, x, phi, True)) < 1e-13
+    X = np.stack([x, np.sin(x)], axis=1)
+    assert relerr(rk.QQard(X, X, (1.4, [0.7, 1.1]), handle=handle), o.rk_QQard(X, X, (1.4, [0.7, 1.1]))) < 1e-13
+
+
+def test_p_Xn_p_dotXn_like_R_tests(handle):
+    # R/tests.R:5-9,33-64: t = seq(-2, 2, 0.2), data exp(t)
+    from gp_b200 import ode_gp_library as lib
+    tn = np.arange(-2, 2.0001, 0.2)
+    Xn = np.exp(tn)
+    phi, sig = (1.2, 1.0), 0.1
+    r = lib.p_dotXn(tn, Xn, phi, sig, handle=handle)
+    rm, rv = o.p_dotXn(tn, Xn, phi, sig)
+    assert relerr(r["condMean"], rm) < 1e-8 and relerr(r["condVar"], rv) < 1e-8
+    r = lib.p_Xn(tn, Xn, phi, sig, handle=handle)
+    rm, rv = o.p_Xn(tn, Xn, phi, sig)
+    assert relerr(r["condMean"], rm) < 1e-8 and relerr(r["condVar"], rv) < 1e-7
+    r = lib.p_dotXn_mnKn(tn, Xn, phi, sig, handle=handle)
+    mn, Kn = o.p_dotXn_solve(tn, Xn, phi, sig)
+    assert relerr(r["mn"], mn) < 1e-8 and relerr(r["Kn"], Kn) < 1e-8
+    # derivative of exp(t) is exp(t): the posterior mean tracks it (the eyeball check of R/tests.R:64-76)
+    assert np.max(np.abs(r["mn"][3:-3] - Xn[3:-3])) < 0.5
+
+
+def test_sample_derivs_draw(handle):
+    from gp_b200 import ode_gp_library as lib
+    ti = np.linspace(0, 10, 120)
+    yn = np.sin(ti) + 0.05 * np.random.default_rng(0).standard_normal(120)
+    draw = lib.sample_derivs((1.0, 1.2, 0.05), yn, ti, rng=np.random.default_rng(1), handle=handle)
+    mu, cov = o.sample_derivs_moments((1.0, 1.2, 0.05), yn, ti)
+    L = np.linalg.cholesky(cov)
+    ref = mu + L @ np.random.default_rng(1).standard_normal(120)
+    assert relerr(draw, ref) < 1e-6
+    assert np.max(np.abs(mu[10:-10] - np.cos(ti[10:-10]))) < 0.2
+
+
+def test_rbf_cov_chol_return_shape(handle):
+    from gp_b200 import covariance as cv
+    out = cv.rbf_cov_chol(np.arange(20) * 1.0, 0.6, handle=handle)
+    assert set(out) == {"L", "dLdl"} and out["L"].shape == (20, 20) and out["L"].flags.f_contiguous
+    Lr, dLr = o.rbf_cov_chol(np.arange(20) * 1.0, 0.6)
+    assert relerr(out["L"], Lr) < 1e-9 and relerr(out["dLdl"], dLr) < 1e-8
+
+
+def test_stan_math_mirror(handle):
+    from gp_b200 import GpB200Error, NotPositiveDefiniteError, stan_math as sm
+    x = np.linspace(0, 10, 100)
+    rng = np.random.default_rng(1)
+    y = np.sin(x) + 0.2 * rng.standard_normal(100)
+    K = sm.cov_exp_quad(x, 1.0, 1.0, 0.04, handle=handle)
+    L = sm.cholesky_decompose(K, handle=handle)
+    assert relerr(L, o.cholesky_decompose(o.gram_se(x, 1.0, 1.0, 0.04))) < 1e-9
+    lp = sm.multi_normal_cholesky_lpdf(y, np.zeros(100), L, handle=handle)
+    assert abs(lp - o.lml(x, y, 1.0, 1.0, 0.2)) < 1e-9 * abs(lp)
+    z = rng.standard_normal(100)
+    assert relerr(sm.multiply_lower_tri(L, z, handle=handle), L @ z) < 1e-12
+    Kbad = K.copy(); Kbad[2, 5] += 1e-6
+    with pytest.raises(GpB200Error):
+        sm.cholesky_decompose(Kbad, handle=handle)
+    Kneg = K.copy(); Kneg[50, 50] = -1
+    with pytest.raises(NotPositiveDefiniteError):
+        sm.cholesky_decompose(Kneg, handle=handle)
+    # lp__ on the unconstrained scale and its gradient (what NUTS consumes)
+    u = np.log([0.9, 1.2, 0.3])
+    lp, g = sm.fit_hyperparameters_lp(x, y, *u, handle=handle)
+    assert abs(lp - o.lp_fit_hyperparameters(x, y, *u)) < 1e-9 * abs(lp)
+    for k in range(3):
+        up, um = u.copy(), u.copy()
+        up[k] += 1e-6; um[k] -= 1e-6
+        fd = (o.lp_fit_hyperparameters(x, y, *up) - o.lp_fit_hyperparameters(x, y, *um)) / 2e-6
+        assert abs(fd - g[k]) < 1e-5 * max(1.0, abs(g[k]))

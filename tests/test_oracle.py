@@ -141,3 +141,11 @@ def test_lp_matches_lml_plus_priors():
     base = o.lml(x, y, 1.2, 0.9, 0.3, drop_constants=True)
     extra = 3 * np.log(0.9) - 4 * 0.9 - 0.5 * 1.2 ** 2 - 0.5 * 0.3 ** 2 + np.log(0.9) + np.log(1.2) + np.log(0.3)
     assert abs(lp - (base + extra)) < 1e-12
+
+
+def test_lapack_route_matches_plain_route():
+    x, y = o.synth_xy(400, 3)
+    for th in o.synth_theta(3, 1):
+        v, g = o.lml_grad(x, y, *th)
+        v2, g2 = o.lml_grad_lapack(x, y, *th)
+        assert abs(v - v2) < 1e-12 * abs(v) and relerr(g2, g) < 1e-11
