@@ -1,0 +1,225 @@
+"""Block-column-cyclic multi-GPU Cholesky / LML of ONE large exact GP.
+
+The reference has nothing like this (its answer to large N is approximation); the
+semantics are those of models/fit_hyperparameters.stan:19-31 at a size where one GPU is too slow.
+
+Layout: the padded matrix (np = ceil(n/128)*128) is cut into panels of `panel_cols` columns; panel p
+belongs to rank p % world and is stored compactly (rows [p*panel_cols, np) only).  Every rank builds
+its own panels of the Gram matrix from the replicated x (no K scatter).
+
+Algorithm (right-looking, look-ahead 1):
+    for p in panels:
+        owner(p) has factored panel p (diagonal block + rows below) -> NCCL broadcast of the panel
+        owner(p+1) first applies panel p to panel p+1, factors it and starts ITS broadcast
+        everybody applies panel p to the rest of its own panels (DMMA GEMM, K = panel_cols)
+so the broadcast of panel p+1 travels over NVLink while the trailing update of panel p runs.
+The only collectives are those panel broadcasts, the small replicated vectors of the forward
+substitution and one all-reduce of (log-det, info) -- torch.distributed (NCCL on GPUs).
+
+The per-rank compute is behind a tiny backend interface so that the schedule (ownership, ordering,
+buffers, collectives) can be exercised with world_size-2 gloo processes on CPU
+(tests/test_block_cyclic.py); on GPUs the backend is the C ABI of include/gpb200.h (gpb200_mg_*).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+TILE = 128
+
+
+def padded(n: int) -> int:
+    return (n + TILE - 1) // TILE * TILE
+
+
+class GpuPanelBackend:
+    """Per-rank compute through libgpb200.so on torch CUDA tensors (device-pointer ABI)."""
+
+    def __init__(self, handle, device):
+        import torch
+        self.torch = torch
+        self.h = handle
+        self.device = device
+        self.lib = handle.lib
+        handle.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def _chk(self, rc, where):
+        self.h._check(rc, where, allow_info=False)
+
+    def empty(self, rows, cols):
+        return self.torch.empty((cols, rows), dtype=self.torch.float64, device=self.device)  # column-major rows x cols
+
+    def vector(self, n, zero=True):
+        f = self.torch.zeros if zero else self.torch.empty
+        return f(n, dtype=self.torch.float64, device=self.device)
+
+    def from_host(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+
+    def info_scalar(self):
+        return self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
+
+    def gram_panel(self, n, x, alpha, rho, diag_add, col0, ncols, P, ldp):
+        self._chk(self.lib.gpb200_mg_gram_panel(self.h._h, n, x.data_ptr(), alpha, rho, diag_add, col0, ncols,
+                                                P.data_ptr(), ldp), "mg_gram_panel")
+
+    def panel_factor(self, n, col0, ncols, P, ldp, info):
+        self._chk(self.lib.gpb200_mg_panel_factor(self.h._h, n, col0, ncols, P.data_ptr(), ldp, info.data_ptr()),
+                  "mg_panel_factor")
+
+    def panel_update(self, n, pcol0, pncols, P, ldp, ccol0, cncols, Cp, ldc):
+        self._chk(self.lib.gpb200_mg_panel_update(self.h._h, n, pcol0, pncols, P.data_ptr(), ldp, ccol0, cncols,
+                                                  Cp.data_ptr(), ldc), "mg_panel_update")
+
+    def panel_trsv(self, n, col0, ncols, P, ldp, y, acc, z, scratch):
+        self._chk(self.lib.gpb200_mg_panel_trsv(self.h._h, n, col0, ncols, P.data_ptr(), ldp, y.data_ptr(),
+                                                acc.data_ptr(), z.data_ptr(), scratch.data_ptr()), "mg_panel_trsv")
+
+    def panel_logdiag(self, n, col0, ncols, P, ldp, out):
+        self._chk(self.lib.gpb200_mg_panel_logdiag(self.h._h, n, col0, ncols, P.data_ptr(), ldp, out.data_ptr()),
+                  "mg_panel_logdiag")
+
+    def to_host(self, t):
+        return t.cpu().numpy()
+
+
+class BlockCyclicGP:
+    """Distributed factorisation and LML of one exact GP with a squared-exponential kernel."""
+
+    def __init__(self, n, panel_cols=1024, backend=None, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n = int(n)
+        self.np_ = padded(self.n)
+        self.pc = min(int(panel_cols), self.np_)
+        if self.pc % TILE:
+            raise ValueError("panel_cols must be a multiple of 128")
+        self.npanels = (self.np_ + self.pc - 1) // self.pc
+        self.be = backend
+        self.panels = {}
+        self.info = None
+
+    # -- geometry -----------------------------------------------------------------------------
+    def owner(self, p):
+        return p % self.world
+
+    def col0(self, p):
+        return p * self.pc
+
+    def ncols(self, p):
+        return min(self.pc, self.np_ - p * self.pc)
+
+    def ld(self, p):
+        return self.np_ - p * self.pc
+
+    def my_panels(self):
+        return [p for p in range(self.npanels) if self.owner(p) == self.rank]
+
+    def _bcast(self, tensor, src, async_op=False):
+        if self.world == 1:
+            return None
+        return self.dist.broadcast(tensor, src=src, group=self.group, async_op=async_op)
+
+    # -- factorisation ------------------------------------------------------------------------
+    def factor(self, x, alpha, rho, sigma, jitter=0.0):
+        """K = cov_exp_quad(x, alpha, rho) + (sigma^2 + jitter) I  ->  L, distributed.  Returns LAPACK info."""
+        be, n = self.be, self.n
+        dx = be.from_host(x)
+        self.info = be.info_scalar()
+        self.panels = {}
+        for p in self.my_panels():
+            P = be.empty(self.ld(p), self.ncols(p))
+            be.gram_panel(n, dx, float(alpha), float(rho), float(sigma) ** 2 + float(jitter), self.col0(p),
+                          self.ncols(p), P, self.ld(p))
+            self.panels[p] = P
+        # receive buffers for the panel being applied and the one in flight (look-ahead 1)
+        recv = [None, None]
+        pending = {}
+
+        def start_bcast(p):
+            own = self.owner(p)
+            if own == self.rank:
+                buf = self.panels[p]
+            else:
+                slot = p % 2
+                need = self.ld(p) * self.ncols(p)
+                if recv[slot] is None or recv[slot].numel() < need:
+                    recv[slot] = be.empty(self.ld(0), self.pc)
+                buf = recv[slot].reshape(-1)[:need].reshape(self.ncols(p), self.ld(p))
+            work = self._bcast(buf, own, async_op=True)
+            pending[p] = (buf, work)
+
+        if self.owner(0) == self.rank:
+            be.panel_factor(n, self.col0(0), self.ncols(0), self.panels[0], self.ld(0), self.info)
+        start_bcast(0)
+        for p in range(self.npanels):
+            buf, work = pending.pop(p)
+            if work is not None:
+                work.wait()
+            nxt = p + 1
+            if nxt < self.npanels:
+                if self.owner(nxt) == self.rank:
+                    be.panel_update(n, self.col0(p), self.ncols(p), buf, self.ld(p), self.col0(nxt), self.ncols(nxt),
+                                    self.panels[nxt], self.ld(nxt))
+                    be.panel_factor(n, self.col0(nxt), self.ncols(nxt), self.panels[nxt], self.ld(nxt), self.info)
+                start_bcast(nxt)
+            for q in self.my_panels():
+                if q > nxt:
+                    be.panel_update(n, self.col0(p), self.ncols(p), buf, self.ld(p), self.col0(q), self.ncols(q),
+                                    self.panels[q], self.ld(q))
+        info = self.info.clone()
+        if self.world > 1:
+            # first failing pivot over all ranks: max over ranks of (info>0 ? BIG - info : 0) keeps the smallest
+            big = 1 << 30
+            enc = (info > 0).to(info.dtype) * (big - info)
+            self.dist.all_reduce(enc, op=self.dist.ReduceOp.MAX, group=self.group)
+            info = (enc > 0).to(info.dtype) * (big - enc)
+        return int(be.to_host(info)[0])
+
+    # -- likelihood ---------------------------------------------------------------------------
+    def lml(self, y):
+        """MVN(y | 0, K) log density with constants (models/fit_hyperparameters.stan:31) from the
+        distributed factor: forward substitution panel by panel (owner solves, replicated vectors are
+        re-broadcast), log-det all-reduced."""
+        be, n = self.be, self.n
+        dy = be.from_host(np.concatenate([np.asarray(y, dtype=np.float64), np.zeros(self.np_ - n)]))
+        acc = be.vector(self.np_)
+        z = be.vector(self.np_)
+        logdet = be.vector(1)
+        scratch = None
+        for p in range(self.npanels):
+            own = self.owner(p)
+            c0, nc = self.col0(p), self.ncols(p)
+            if own == self.rank:
+                if scratch is None:
+                    scratch = be.empty(self.ld(0), TILE)
+                be.panel_trsv(n, c0, nc, self.panels[p], self.ld(p), dy, acc, z, scratch)
+                be.panel_logdiag(n, c0, nc, self.panels[p], self.ld(p), logdet)
+            if self.world > 1:
+                self._bcast(z[c0:c0 + nc], own)
+                if c0 + nc < self.np_:
+                    self._bcast(acc[c0 + nc:], own)
+        if self.world > 1:
+            self.dist.all_reduce(logdet, op=self.dist.ReduceOp.SUM, group=self.group)
+        zh = be.to_host(z)[:n]
+        ld = float(be.to_host(logdet)[0])
+        return -0.5 * n * math.log(2.0 * math.pi) - ld - 0.5 * float(zh @ zh)
+
+    def gather_factor(self):
+        """Dense lower factor on the host of every rank (tests only; O(N^2) traffic)."""
+        L = np.zeros((self.np_, self.np_))
+        for p in range(self.npanels):
+            own = self.owner(p)
+            c0, nc, ld = self.col0(p), self.ncols(p), self.ld(p)
+            if own == self.rank:
+                buf = self.panels[p]
+            else:
+                buf = self.be.empty(ld, nc)
+            self._bcast(buf, own)
+            blk = self.be.to_host(buf).reshape(nc, ld).T   # rows [c0, np) x nc
+            L[c0:, c0:c0 + nc] = blk
+        return np.tril(L)[:self.n, :self.n]

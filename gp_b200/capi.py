@@ -33,6 +33,7 @@ SIGNATURES = {
     "gpb200_launch_count": (_ll, [_h]),
     "gpb200_version": (C.c_int, []),
     "gpb200_set_workspace_limit": (C.c_int, [_h, _ll]),
+    "gpb200_set_chol_panel_tiles": (C.c_int, [_h, C.c_int]),
     "gpb200_set_profiling": (C.c_int, [_h, C.c_int]),
     "gpb200_get_profile": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
     "gpb200_kernel_eval": (C.c_int, [_h, C.c_int, _ll, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
@@ -60,6 +61,14 @@ SIGNATURES = {
                                       C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "gpb200_cond_mvn": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int]),
+    "gpb200_mg_gram_panel": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                       C.c_void_p, _ll]),
+    "gpb200_mg_panel_factor": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p]),
+    "gpb200_mg_panel_update": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_int, C.c_int, C.c_void_p,
+                                         _ll]),
+    "gpb200_mg_panel_trsv": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "gpb200_mg_panel_logdiag": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p]),
 }
 
 _lib = None
@@ -157,6 +166,9 @@ class Handle:
         return int(self.lib.gpb200_launch_count(self._h))
 
     PROFILE_CLASSES = ("gemm", "potrf_tile", "trsm_tile", "gram", "solve", "other")
+
+    def set_chol_panel_tiles(self, tiles: int):
+        self._check(self.lib.gpb200_set_chol_panel_tiles(self._h, int(tiles)), "set_chol_panel_tiles")
 
     def set_profiling(self, on: bool):
         self._check(self.lib.gpb200_set_profiling(self._h, int(bool(on))), "set_profiling")

@@ -61,7 +61,7 @@ int ws_reserve(Handle *h, size_t bytes, Arena *a) {
 // ---------------------------------------------------------------------------------------------
 // task lists (host-built once per tile count, cached on the device)
 // ---------------------------------------------------------------------------------------------
-enum TaskKind { TK_CHOL = 1, TK_TRTRI_S, TK_TRTRI_W, TK_LAUUM, TK_TAN_T1, TK_TAN_A, TK_TAN_LDOT, TK_COND_V,
+enum TaskKind { TK_CHOL = 1, TK_CHOL_TRAIL, TK_TRTRI_S, TK_TRTRI_W, TK_LAUUM, TK_TAN_T1, TK_TAN_A, TK_TAN_LDOT, TK_COND_V,
                 TK_COND_COV, TK_MUL_WB, TK_MUL_WTB };
 
 struct TaskList {
@@ -103,18 +103,33 @@ void sort_desc(std::vector<TileTask> &v, size_t from) {
   std::stable_sort(v.begin() + from, v.end(), [](const TileTask &x, const TileTask &y) { return x.k_len > y.k_len; });
 }
 
-// left-looking Cholesky: step j updates block column j with everything to its left
-int tasks_chol(Handle *h, int nt, TaskList *out) {
-  const long long key = tkey(TK_CHOL, nt);
-  if (cached(h, key, out)) return 0;
-  std::vector<TileTask> t;
-  std::vector<int> off(1, 0);
+// Cholesky task lists.  Panels of `pt` tile columns: inside a panel the factorisation is
+// left-looking (step j updates block column j with the panel's columns to its left, K = (j-p0)*128);
+// after a panel is complete one right-looking launch applies it to everything to its right
+// (K = pt*128).  pt = nt is the pure left-looking algorithm used for large batches; a narrow panel
+// gives a single large matrix enough tiles per launch to fill 148 SMs.
+int tasks_chol(Handle *h, int nt, int pt, TaskList *upd, TaskList *trail) {
+  const long long k1 = tkey(TK_CHOL, nt, pt), k2 = tkey(TK_CHOL_TRAIL, nt, pt);
+  if (cached(h, k1, upd) && cached(h, k2, trail)) return 0;
+  std::vector<TileTask> t, tt;
+  std::vector<int> off(1, 0), offt(1, 0);
   for (int j = 0; j < nt; j++) {
-    if (j > 0)
-      for (int i = j; i < nt; i++) t.push_back({i * TILE, 0, j * TILE, 0, i * TILE, j * TILE, j * TILE, i == j});
+    const int p0 = (j / pt) * pt;
+    if (j > p0)
+      for (int i = j; i < nt; i++)
+        t.push_back({i * TILE, p0 * TILE, j * TILE, p0 * TILE, i * TILE, j * TILE, (j - p0) * TILE, i == j});
     off.push_back((int)t.size());
   }
-  return upload_tasks(h, key, t, off, out);
+  for (int p0 = 0; p0 < nt; p0 += pt) {
+    const int p1 = std::min(nt, p0 + pt);
+    for (int jj = p1; jj < nt; jj++)
+      for (int i = jj; i < nt; i++)
+        tt.push_back({i * TILE, p0 * TILE, jj * TILE, p0 * TILE, i * TILE, jj * TILE, (p1 - p0) * TILE, i == jj});
+    offt.push_back((int)tt.size());
+  }
+  int rc = upload_tasks(h, k1, t, off, upd);
+  if (rc) return rc;
+  return upload_tasks(h, k2, tt, offt, trail);
 }
 
 struct Node { int lo, mid, hi, level; };
@@ -174,21 +189,29 @@ int tasks_lauum(Handle *h, int nt, TaskList *out) {
 // ---------------------------------------------------------------------------------------------
 MatRef mref(double *p, long long ld, long long stride) { return MatRef{p, ld, stride}; }
 
-// Batched left-looking tiled Cholesky, in place on Lbuf (np x np per item, lower tiles valid).
+// Batched tiled Cholesky, in place on Lbuf (np x np per item, lower tiles valid on entry).
+// Panel width: pure left-looking when the batch alone fills the GPU, 8-tile (1024-column) panels
+// with right-looking trailing updates otherwise.
+int chol_panel_tiles(int nt, int batch) {
+  if (batch >= 64 || nt <= 8) return nt;
+  return 8;
+}
+
 int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev, double *dvec) {
   const int nt = np / TILE;
-  TaskList tl;
-  int rc = tasks_chol(h, nt, &tl);
+  const int pt = h->chol_panel_override > 0 ? std::min(nt, h->chol_panel_override) : chol_panel_tiles(nt, batch);
+  TaskList tl, tr;
+  int rc = tasks_chol(h, nt, pt, &tl, &tr);
   if (rc) return rc;
+  GemmParams p{};
+  p.A = mref(Lbuf, np, stride);
+  p.B = mref(Lbuf, np, stride);
+  p.C = mref(Lbuf, np, stride);
+  p.C0 = mref(Lbuf, np, stride);
+  p.alpha = -1.0;
+  p.beta = 1.0;
   for (int j = 0; j < nt; j++) {
-    if (j > 0) {
-      GemmParams p{};
-      p.A = mref(Lbuf, np, stride);
-      p.B = mref(Lbuf, np, stride);
-      p.C = mref(Lbuf, np, stride);
-      p.C0 = mref(Lbuf, np, stride);
-      p.alpha = -1.0;
-      p.beta = 1.0;
+    if (tl.count(j) > 0) {
       p.tasks = tl.at(j);
       rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(j), batch);
       if (rc) return rc;
@@ -197,6 +220,12 @@ int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int b
     if (rc) return rc;
     rc = launch_trsm_tiles(h, Lbuf, np, stride, j, nt - 1 - j, batch);
     if (rc) return rc;
+    if ((j + 1) % pt == 0 && j + 1 < nt) {
+      const int panel = j / pt;
+      p.tasks = tr.at(panel);
+      rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tr.count(panel), batch);
+      if (rc) return rc;
+    }
   }
   (void)dvec;
   return 0;
@@ -353,6 +382,13 @@ extern "C" long long gpb200_launch_count(gpb200_handle_t h) { return h ? h->laun
 extern "C" int gpb200_set_workspace_limit(gpb200_handle_t h, long long bytes) {
   if (!h) return -1;
   h->ws_limit = bytes;
+  return 0;
+}
+
+// test/tuning knob: force the Cholesky panel width in 128-column tiles (0 = automatic)
+extern "C" int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles) {
+  if (!h || tiles < 0) return -1;
+  h->chol_panel_override = tiles;
   return 0;
 }
 
@@ -649,7 +685,7 @@ extern "C" int gpb200_mvn_chol_lpdf(gpb200_handle_t h, int n, const double *y, c
   if (ldl < std::max(1, n)) BAD_ARG(h, 6, "mvn_chol_lpdf: ldl < n");
   const int np = round_up(std::max(n, 1), TILE);
   Arena a;
-  RC(ws_reserve(h, 3 * pad256((size_t)np * np * 8) + 6 * pad256(np * 8), &a));
+  RC(ws_reserve(h, 3 * pad256((size_t)np * np * 8) + 8 * pad256(np * 8), &a));
   double *Lbuf = nullptr;
   RC(stage_lower(h, a, n, np, L, ldl, &Lbuf));
   double *Wd = a.take<double>((size_t)np * np);
@@ -657,7 +693,8 @@ extern "C" int gpb200_mvn_chol_lpdf(gpb200_handle_t h, int n, const double *y, c
   RC(to_device(h, y, dy, n));
   if (mu) RC(to_device(h, mu, dmu, n));
   RC(launch_tile_inverse(h, Lbuf, Wd, np, 0, np / TILE, 1));
-  RC(launch_trsv_blocked(h, np, Lbuf, Wd, 0, dy, 0, mu ? dmu : nullptr, n, dz, 0, 1));
+  double *dacc = a.take<double>(np);
+  RC(launch_trsv_sweep(h, np, Lbuf, Wd, 0, dy, 0, mu ? dmu : nullptr, n, dz, dacc, np, 1));
   RC(launch_sumsq_logdiag(h, n, dz, Lbuf, np, out2));
   double r[2];
   GPB_CUDA(h, cudaMemcpyAsync(r, out2, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
@@ -743,7 +780,8 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
       RC(launch_gemm(h, LAYOUT_TN, EPI_TRACE, p, ntasks, bc));
     } else {
       RC(launch_tile_inverse(h, Lbuf, Sbuf, np, mat, nt, bc));
-      RC(launch_trsv_blocked(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, np, bc));
+      if (bc >= 32) RC(launch_trsv_blocked(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, np, bc));
+      else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
     }
     RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
   }
@@ -1036,4 +1074,149 @@ extern "C" int gpb200_cond_mvn(gpb200_handle_t h, int ng, int nd, const double *
   }
   RC(finish(h));
   return hinfo;
+}
+
+// =================================================================================================
+// (e) building blocks of the block-cyclic multi-GPU Cholesky (config 5).  DEVICE pointers only.
+// A "panel" is a block column of the padded matrix stored compactly: rows [col0, np) x ncols
+// columns, leading dimension ldp >= np - col0.  The collective (panel broadcast over NCCL) lives
+// in gp_b200/block_cyclic.py; these calls are the per-rank compute between collectives.
+// =================================================================================================
+namespace {
+long long mgkey(int kind, int a, int b, int c, int d) {
+  return ((long long)kind << 52) | ((long long)(a & 0x1fff) << 39) | ((long long)(b & 0x1fff) << 26) |
+         ((long long)(c & 0x1fff) << 13) | (long long)(d & 0x1fff);
+}
+enum { TK_MG_FACTOR = 40, TK_MG_UPDATE = 41 };
+
+int mg_check_panel(Handle *h, int n, int col0, int ncols, long long ldp, int *np_out) {
+  const int np = round_up(n, TILE);
+  if (n < 1 || col0 < 0 || ncols < TILE || (col0 % TILE) || (ncols % TILE) || col0 + ncols > np)
+    BAD_ARG(h, 3, "mg: panel must be tile aligned and inside the padded matrix");
+  if (ldp < np - col0 || (ldp & 1)) BAD_ARG(h, 6, "mg: ldp must be even and >= np - col0");
+  *np_out = np;
+  return 0;
+}
+}  // namespace
+
+extern "C" int gpb200_mg_gram_panel(gpb200_handle_t h, int n, const double *x, double alpha, double rho,
+                                    double diag_add, int col0, int ncols, double *P, long long ldp) {
+  CHECK_H(h);
+  int np;
+  RC(mg_check_panel(h, n, col0, ncols, ldp, &np));
+  return launch_gram_se_panel(h, n, np, x, alpha, rho, diag_add, col0, ncols, P, ldp);
+}
+
+extern "C" int gpb200_mg_panel_factor(gpb200_handle_t h, int n, int col0, int ncols, double *P, long long ldp,
+                                      int *info_dev) {
+  CHECK_H(h);
+  int np;
+  RC(mg_check_panel(h, n, col0, ncols, ldp, &np));
+  const int ntp = ncols / TILE, nrt = (np - col0) / TILE;
+  TaskList tl;
+  const long long key = mgkey(TK_MG_FACTOR, nrt, ntp, 0, 0);
+  if (!cached(h, key, &tl)) {
+    std::vector<TileTask> t;
+    std::vector<int> off(1, 0);
+    for (int jl = 0; jl < ntp; jl++) {
+      if (jl > 0)
+        for (int i = jl; i < nrt; i++) t.push_back({i * TILE, 0, jl * TILE, 0, i * TILE, jl * TILE, jl * TILE, i == jl});
+      off.push_back((int)t.size());
+    }
+    RC(upload_tasks(h, key, t, off, &tl));
+  }
+  GemmParams p{};
+  p.A = mref(P, ldp, 0);
+  p.B = mref(P, ldp, 0);
+  p.C = mref(P, ldp, 0);
+  p.C0 = mref(P, ldp, 0);
+  p.alpha = -1.0;
+  p.beta = 1.0;
+  for (int jl = 0; jl < ntp; jl++) {
+    if (tl.count(jl) > 0) {
+      p.tasks = tl.at(jl);
+      RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(jl), 1));
+    }
+    const long long doff = (long long)jl * TILE * (ldp + 1);
+    RC(launch_potrf_tile_at(h, P, ldp, 0, doff, col0 + jl * TILE, n, 1, info_dev));
+    RC(launch_trsm_tiles_at(h, P, ldp, 0, doff, doff + TILE, nrt - 1 - jl, 1));
+  }
+  return 0;
+}
+
+extern "C" int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P, long long ldp,
+                                      int ccol0, int cncols, double *Cp, long long ldc) {
+  CHECK_H(h);
+  int np;
+  RC(mg_check_panel(h, n, pcol0, pncols, ldp, &np));
+  RC(mg_check_panel(h, n, ccol0, cncols, ldc, &np));
+  if (ccol0 < pcol0 + pncols) BAD_ARG(h, 7, "mg_panel_update: the target panel must lie right of the source panel");
+  const int nt = np / TILE, d = (ccol0 - pcol0) / TILE, cnt = cncols / TILE, crt = nt - ccol0 / TILE, pk = pncols / TILE;
+  TaskList tl;
+  const long long key = mgkey(TK_MG_UPDATE, d, cnt, crt, pk);
+  if (!cached(h, key, &tl)) {
+    std::vector<TileTask> t;
+    for (int jl = 0; jl < cnt; jl++)
+      for (int il = jl; il < crt; il++)  // il, jl: tile coordinates local to the target panel
+        t.push_back({(il + d) * TILE, 0, (jl + d) * TILE, 0, il * TILE, jl * TILE, pk * TILE, il == jl});
+    std::vector<int> off = {0, (int)t.size()};
+    RC(upload_tasks(h, key, t, off, &tl));
+  }
+  GemmParams p{};
+  p.A = mref(const_cast<double *>(P), ldp, 0);
+  p.B = mref(const_cast<double *>(P), ldp, 0);
+  p.C = mref(Cp, ldc, 0);
+  p.C0 = mref(Cp, ldc, 0);
+  p.alpha = -1.0;
+  p.beta = 1.0;
+  p.tasks = tl.at(0);
+  return launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(0), 1);
+}
+
+// forward substitution through one factored panel: z[pcol0 .. +ncols) = solve, acc[rows below] +=
+// L z.  y, acc, z are replicated device vectors of length np; wscratch holds one inverted tile
+// (ldp x 128 doubles).
+extern "C" int gpb200_mg_panel_trsv(gpb200_handle_t h, int n, int col0, int ncols, const double *P, long long ldp,
+                                    const double *y, double *acc, double *z, double *wscratch) {
+  CHECK_H(h);
+  int np;
+  RC(mg_check_panel(h, n, col0, ncols, ldp, &np));
+  const int ntp = ncols / TILE, nrt = (np - col0) / TILE;
+  for (int jl = 0; jl < ntp; jl++) {
+    const long long doff = (long long)jl * TILE * (ldp + 1);
+    RC(launch_tile_inverse_at(h, P, ldp, doff, 0, wscratch, 0, 0, 0, 1, 1));
+    RC(launch_trsv_diag(h, ldp, 0, col0 + jl * TILE, wscratch, 0, y, 0, nullptr, n, acc, z, 0, 1));
+    RC(launch_trsv_update(h, ldp, doff + TILE, col0 + jl * TILE, col0 + (jl + 1) * TILE, nrt - 1 - jl, P, 0, z, acc, 0, 1));
+  }
+  return 0;
+}
+
+namespace {
+__global__ void panel_logdiag_kernel(int n, int col0, int ncols, const double *__restrict__ P, long long ldp,
+                                     double *__restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int c = threadIdx.x; c < ncols; c += 256)
+    if (col0 + c < n) s += log(P[c + (long long)c * ldp]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    out[0] += t;
+  }
+}
+}  // namespace
+
+// out[0] += sum_{i in panel, i < n} log L_ii  (device scalar, accumulated across this rank's panels)
+extern "C" int gpb200_mg_panel_logdiag(gpb200_handle_t h, int n, int col0, int ncols, const double *P, long long ldp,
+                                       double *out) {
+  CHECK_H(h);
+  int np;
+  RC(mg_check_panel(h, n, col0, ncols, ldp, &np));
+  ProfScope ps__(h, PC_OTHER);
+  panel_logdiag_kernel<<<1, 256, 0, h->stream>>>(n, col0, ncols, P, ldp, out);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
 }

@@ -49,6 +49,7 @@ struct Handle {
   int device_ptrs = 0;
   long long launches = 0;
   long long ws_limit = 0;
+  int chol_panel_override = 0;
   char err[512] = {0};
   // grow-only device workspace
   void *ws = nullptr;
@@ -128,6 +129,12 @@ int launch_trsm_tiles(Handle *h, double *L, long long ld, long long stride, int 
                       int ntiles_below, int batch);
 int launch_tile_inverse(Handle *h, const double *L, double *W, long long ld, long long stride,
                         int ntiles, int batch);
+int launch_potrf_tile_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, int index_base,
+                         int n, int batch, int *info);
+int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, long long c_off,
+                         int ntiles, int batch);
+int launch_tile_inverse_at(Handle *h, const double *L, long long ld, long long l_off, long long l_step, double *W,
+                           long long w_off, long long w_step, long long stride, int ntiles, int batch);
 int panel_smem_setup(Handle *h);
 
 }  // namespace gpb

@@ -108,6 +108,40 @@ __global__ void __launch_bounds__(256) gram_se_batched_kernel(int n, int np, con
   }
 }
 
+// ---- block-column panel of the padded SE Gram for the block-cyclic multi-GPU Cholesky ----------
+// P holds rows [col0, np) x columns [col0, col0+ncols) compactly (leading dimension ldp = np - col0);
+// tiles strictly above the diagonal are skipped.  x is replicated on every GPU: no K scatter.
+__global__ void __launch_bounds__(256) gram_se_panel_kernel(int n, int np, const double *__restrict__ x, double alpha,
+                                                           double rho, double dadd, int col0, double *__restrict__ P,
+                                                           long long ldp) {
+  const int r0 = col0 + blockIdx.x * TILE, c0 = col0 + blockIdx.y * TILE;
+  if (r0 < c0) return;
+  __shared__ double xs[TILE], ys[TILE];
+  const int tid = threadIdx.x;
+  if (tid < TILE) xs[tid] = (r0 + tid < n) ? x[r0 + tid] : 0.0;
+  else ys[tid - TILE] = (c0 + tid - TILE < n) ? x[c0 + tid - TILE] : 0.0;
+  __syncthreads();
+  const double a2 = alpha * alpha, nh = -0.5 / (rho * rho);
+  const int rl = 2 * (tid & 63), cq = tid >> 6;
+#pragma unroll 4
+  for (int s = 0; s < 32; s++) {
+    const int cl = cq + 4 * s;
+    const int j = c0 + cl;
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = r0 + rl + e;
+      if (i < n && j < n) {
+        const double d = xs[rl + e] - ys[cl];
+        v[e] = (i == j) ? a2 + dadd : a2 * exp(d * d * nh);
+      } else {
+        v[e] = (i == j) ? 1.0 : 0.0;
+      }
+    }
+    *reinterpret_cast<double2 *>(P + (r0 - col0 + rl) + (long long)(j - col0) * ldp) = make_double2(v[0], v[1]);
+  }
+}
+
 // ---- rbf_cov_chol Gram + tangent (covariance.cpp:15-25): padded, full square -------------------
 __global__ void __launch_bounds__(256) gram_rbf_tangent_kernel(int n, int np, const double *__restrict__ x, double l,
                                                               double jitter, double *__restrict__ S,
@@ -213,6 +247,15 @@ int launch_gram_se_batched(Handle *h, int n, int np, const double *x, long long 
   dim3 grid(nt * nt, batch);
   ProfScope ps__(h, PC_GRAM);
   gram_se_batched_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, x_stride, theta, jitter, lower_only, K, stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gram_se_panel(Handle *h, int n, int np, const double *x, double alpha, double rho, double diag_add,
+                         int col0, int ncols, double *P, long long ldp) {
+  dim3 grid((np - col0) / TILE, ncols / TILE);
+  ProfScope ps__(h, PC_GRAM);
+  gram_se_panel_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, alpha, rho, diag_add, col0, P, ldp);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

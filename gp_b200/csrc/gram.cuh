@@ -26,6 +26,16 @@ int launch_trmv_lower_t(Handle *h, int np, const double *W, long long stride, co
                         double *a, long long a_stride, int batch);
 int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
                         long long y_stride, const double *mu, int n_valid, double *z, long long z_stride, int batch);
+int launch_trsv_diag(Handle *h, long long ldw, long long w_off, int row0, const double *Wdiag, long long stride,
+                     const double *y, long long y_stride, const double *mu, int n_valid, const double *acc, double *z,
+                     long long z_stride, int batch);
+int launch_trsv_update(Handle *h, long long ld, long long l_off, int z_row0, int acc_row0, int ntiles, const double *L,
+                       long long stride, const double *z, double *acc, long long z_stride, int batch);
+int launch_gram_se_panel(Handle *h, int n, int np, const double *x, double alpha, double rho, double diag_add,
+                         int col0, int ncols, double *P, long long ldp);
+int launch_trsv_sweep(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
+                      long long y_stride, const double *mu, int n_valid, double *z, double *acc, long long z_stride,
+                      int batch);
 int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec, const double *z, const double *a,
                     const double *partial, int ntasks, const double *theta, double *lml, double *grad, int batch);
 int launch_pack(Handle *h, int rows, int cols, const double *src, long long lds, int rp, int cp, double *dst,

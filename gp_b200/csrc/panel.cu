@@ -22,12 +22,13 @@ __device__ __forceinline__ void dmma884p(double (&c)[2], double a, double b) {
 // POTRF of one 128x128 tile.  256 threads = 16x16 grid; thread (ti,tj) owns A[ti+16a][tj+16b].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
-potrf_tile_kernel(double *__restrict__ Lbase, long long ld, long long stride, int tile_idx, int n, int *info) {
+potrf_tile_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
+                  int n, int *info) {
   __shared__ double col[2][TILE];
   __shared__ int s_info;
   const int tid = threadIdx.x;
   const int ti = tid & 15, tj = tid >> 4;
-  double *T = Lbase + (long long)blockIdx.x * stride + (long long)tile_idx * TILE * (ld + 1);
+  double *T = Lbase + (long long)blockIdx.x * stride + diag_off;
   double r[8][8];
 #pragma unroll
   for (int b = 0; b < 8; b++)
@@ -51,7 +52,7 @@ potrf_tile_kernel(double *__restrict__ Lbase, long long ld, long long stride, in
     const double piv = cbuf[k];
     if (!(piv > 0.0)) {
       // non-positive (or NaN) pivot: record the first one, keep going so the CTA stays in step
-      if (tid == 0 && s_info == 0) s_info = tile_idx * TILE + k + 1;
+      if (tid == 0 && s_info == 0) s_info = index_base + k + 1;
     }
     const double dgl = sqrt(piv);
     const double inv = 1.0 / dgl;
@@ -112,20 +113,16 @@ constexpr int TRSM_SMEM_BYTES = (TILE * LD_L + TILE) * (int)sizeof(double);
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 1)
-trsm_tile_kernel(const double *Ldiag_base, double *Cbase, long long ld,
-                 long long stride, int tile_col, int tiles_per_item) {
+trsm_tile_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long stride, long long diag_off,
+                 long long diag_step, long long c_off, long long c_step) {
   extern __shared__ __align__(16) double sm[];
   double *Ls = sm;                     // Ls[k*LD_L + n] = L[n][k]
   double *invd = sm + TILE * LD_L;     // 1 / L[n][n]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int item = blockIdx.y;
-  int dtile, rtile;
-  if (MODE == 0) { dtile = tile_col; rtile = tile_col + 1 + blockIdx.x; }
-  else { dtile = blockIdx.x; rtile = blockIdx.x; }
-  const double *Ld = Ldiag_base + (long long)item * stride + (long long)dtile * TILE * (ld + 1);
-  double *Ct = Cbase + (long long)item * stride + (long long)rtile * TILE + (long long)dtile * TILE * ld;
-  (void)tiles_per_item;
+  const double *Ld = Ldiag_base + (long long)item * stride + diag_off + (long long)blockIdx.x * diag_step;
+  double *Ct = Cbase + (long long)item * stride + c_off + (long long)blockIdx.x * c_step;
 
   // stage the diagonal tile (column-major copy, 16B vectors)
   for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
@@ -220,28 +217,48 @@ int panel_smem_setup(Handle *h) {
   return 0;
 }
 
-int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n, int batch, int *info) {
+int launch_potrf_tile_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, int index_base,
+                         int n, int batch, int *info) {
   ProfScope ps__(h, PC_POTRF);
-  potrf_tile_kernel<<<batch, 256, 0, h->stream>>>(L, ld, stride, tile_idx, n, info);
+  potrf_tile_kernel<<<batch, 256, 0, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n, int batch, int *info) {
+  return launch_potrf_tile_at(h, L, ld, stride, (long long)tile_idx * TILE * (ld + 1), tile_idx * TILE, n, batch, info);
+}
+
+// X = C L^-T for `ntiles` consecutive 128-row tiles starting at element offset c_off (tile step = 128
+// rows), against the diagonal tile at element offset diag_off.
+int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, long long c_off,
+                         int ntiles, int batch) {
+  if (ntiles <= 0) return 0;
+  dim3 grid(ntiles, batch);
+  ProfScope ps__(h, PC_TRSM);
+  trsm_tile_kernel<0><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, 0, c_off, TILE);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
 
 int launch_trsm_tiles(Handle *h, double *L, long long ld, long long stride, int tile_col, int ntiles_below, int batch) {
-  if (ntiles_below <= 0) return 0;
-  dim3 grid(ntiles_below, batch);
+  return launch_trsm_tiles_at(h, L, ld, stride, (long long)tile_col * TILE * (ld + 1),
+                              (long long)(tile_col + 1) * TILE + (long long)tile_col * TILE * ld, ntiles_below, batch);
+}
+
+// inverse of `ntiles` diagonal tiles: L tiles at l_off + t*l_step, W tiles at w_off + t*w_step
+int launch_tile_inverse_at(Handle *h, const double *L, long long ld, long long l_off, long long l_step, double *W,
+                           long long w_off, long long w_step, long long stride, int ntiles, int batch) {
+  dim3 grid(ntiles, batch);
   ProfScope ps__(h, PC_TRSM);
-  trsm_tile_kernel<0><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, L, ld, stride, tile_col, 0);
+  trsm_tile_kernel<1><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, W, ld, stride, l_off, l_step, w_off, w_step);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
 
 int launch_tile_inverse(Handle *h, const double *L, double *W, long long ld, long long stride, int ntiles, int batch) {
-  dim3 grid(ntiles, batch);
-  ProfScope ps__(h, PC_TRSM);
-  trsm_tile_kernel<1><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, W, ld, stride, 0, ntiles);
-  GPB_LAUNCH_CHECK(h);
-  return 0;
+  const long long step = (long long)TILE * (ld + 1);
+  return launch_tile_inverse_at(h, L, ld, 0, step, W, 0, step, stride, ntiles, batch);
 }
 
 }  // namespace gpb

@@ -78,36 +78,40 @@ __global__ void __launch_bounds__(256) trmv_lower_t_kernel(int np, const double 
 
 // Blocked forward substitution L z = (y - mu), one CTA per batch item.  Per 128-row block:
 // s = rhs_j - L[j, 0:j] z[0:j] (two k-halves per row), then z_j = Wdiag_j s with the pre-inverted
-// diagonal tile.
+// diagonal tile.  z lives in global memory (written and re-read by this CTA only, ordered by the
+// block barriers), so any n fits.
 __global__ void __launch_bounds__(256) trsv_blocked_kernel(int np, const double *__restrict__ L,
                                                           const double *__restrict__ Wdiag, long long stride,
                                                           const double *__restrict__ y, long long y_stride,
                                                           const double *__restrict__ mu, int n_valid,
-                                                          double *__restrict__ z, long long z_stride) {
-  extern __shared__ double zs[];  // np + 2*128
-  double *part = zs + np;
-  double *sv = part + TILE;
+                                                          double *z, long long z_stride) {
+  __shared__ double part[TILE];
+  __shared__ double sv[TILE];
   const long long b = blockIdx.x;
   const double *Lb = L + b * stride, *Wb = Wdiag + b * stride;
   const double *yb = y + b * y_stride;
+  double *zb = z + b * z_stride;
   const int tid = threadIdx.x, r = tid & 127, half = tid >> 7;
   const int nt = np / TILE;
   for (int j = 0; j < nt; j++) {
     const int i = j * TILE + r;
     const int kmax = j * TILE;
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const double *lp = Lb + i + (long long)half * np;
-    for (int k = half; k < kmax; k += 4) {
-      s0 = fma(lp[0], zs[k], s0);
-      s1 = fma(lp[2LL * np], zs[k + 2], s1);
-      lp += 4LL * np;
+    for (int k = half; k < kmax; k += 8) {
+      s0 = fma(lp[0], zb[k], s0);
+      s1 = fma(lp[2LL * np], zb[k + 2], s1);
+      s2 = fma(lp[4LL * np], zb[k + 4], s2);
+      s3 = fma(lp[6LL * np], zb[k + 6], s3);
+      lp += 8LL * np;
     }
-    if (half == 1) part[r] = s0 + s1;
+    const double ssum = (s0 + s1) + (s2 + s3);
+    if (half == 1) part[r] = ssum;
     __syncthreads();
     if (half == 0) {
       double rhs = 0.0;
       if (i < n_valid) rhs = yb[i] - (mu ? mu[i] : 0.0);
-      sv[r] = rhs - (s0 + s1 + part[r]);
+      sv[r] = rhs - (ssum + part[r]);
     }
     __syncthreads();
     // z_j = Wdiag_j * sv  (lower-triangular 128x128, strict upper is zero)
@@ -119,13 +123,62 @@ __global__ void __launch_bounds__(256) trsv_blocked_kernel(int np, const double 
     }
     if (half == 1) part[r] = t0 + t1;
     __syncthreads();
-    if (half == 0) {
-      const double v = t0 + t1 + part[r];
-      zs[i] = v;
-      z[b * z_stride + i] = v;
-    }
+    if (half == 0) zb[i] = t0 + t1 + part[r];
     __syncthreads();
   }
+}
+
+// Column-sweep forward substitution for small batches (one large matrix): per 128-column block j
+//   trsv_diag:    z_j = Wdiag_j (rhs_j - acc_j)                       one CTA per item
+//   trsv_update:  acc_i += L[i, j] z_j for every tile row i > j        (nt-1-j) CTAs per item
+// so that the N^2/2 read of L is spread over the whole GPU instead of one CTA.
+__global__ void __launch_bounds__(128) trsv_diag_kernel(long long ldw, long long w_off, int row0,
+                                                       const double *__restrict__ Wdiag, long long stride,
+                                                       const double *__restrict__ y, long long y_stride,
+                                                       const double *__restrict__ mu, int n_valid,
+                                                       const double *__restrict__ acc, double *__restrict__ z,
+                                                       long long z_stride) {
+  __shared__ double sv[TILE];
+  const long long b = blockIdx.x;
+  const int r = threadIdx.x, i = row0 + r;
+  double rhs = 0.0;
+  if (i < n_valid) rhs = y[b * y_stride + i] - (mu ? mu[i] : 0.0);
+  sv[r] = rhs - acc[b * z_stride + i];
+  __syncthreads();
+  const double *wd = Wdiag + b * stride + w_off;
+  double t0 = 0.0, t1 = 0.0;
+  for (int k = 0; k < TILE; k += 2) {
+    t0 = fma(wd[r + (long long)k * ldw], sv[k], t0);
+    t1 = fma(wd[r + (long long)(k + 1) * ldw], sv[k + 1], t1);
+  }
+  z[b * z_stride + i] = t0 + t1;
+}
+
+// acc[acc_row0 + 128*blockIdx.x + r] += sum_k L[l_off + 128*blockIdx.x + r + k*ld] * z[z_row0 + k]
+__global__ void __launch_bounds__(256) trsv_update_kernel(long long ld, long long l_off, int z_row0, int acc_row0,
+                                                         const double *__restrict__ L, long long stride,
+                                                         const double *__restrict__ z, double *__restrict__ acc,
+                                                         long long z_stride) {
+  __shared__ double zs[TILE];
+  __shared__ double part[TILE];
+  const long long b = blockIdx.y;
+  const int tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+  if (tid < TILE) zs[tid] = z[b * z_stride + z_row0 + tid];
+  __syncthreads();
+  const double *lp = L + b * stride + l_off + (long long)blockIdx.x * TILE + r + (long long)half * ld;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+  for (int k = half; k < TILE; k += 8) {
+    s0 = fma(lp[0], zs[k], s0);
+    s1 = fma(lp[2LL * ld], zs[k + 2], s1);
+    s2 = fma(lp[4LL * ld], zs[k + 4], s2);
+    s3 = fma(lp[6LL * ld], zs[k + 6], s3);
+    lp += 8LL * ld;
+  }
+  const double ssum = (s0 + s1) + (s2 + s3);
+  if (half == 1) part[r] = ssum;
+  __syncthreads();
+  if (half == 0) acc[b * z_stride + acc_row0 + blockIdx.x * TILE + r] += ssum + part[r];
 }
 
 // Deterministic finalisation, one CTA per batch item.
@@ -297,19 +350,44 @@ int launch_trmv_lower_t(Handle *h, int np, const double *W, long long stride, co
 
 int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
                         long long y_stride, const double *mu, int n_valid, double *z, long long z_stride, int batch) {
-  const size_t smem = (size_t)(np + 2 * TILE) * sizeof(double);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    GPB_CUDA(h, cudaFuncSetAttribute(trsv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
-  }
-  if (smem > 227 * 1024) {
-    snprintf(h->err, sizeof(h->err), "trsv_blocked: n too large for the shared-memory solution vector");
-    return -3;
-  }
   ProfScope ps__(h, PC_SOLVE);
-  trsv_blocked_kernel<<<batch, 256, smem, h->stream>>>(np, L, Wdiag, stride, y, y_stride, mu, n_valid, z, z_stride);
+  trsv_blocked_kernel<<<batch, 256, 0, h->stream>>>(np, L, Wdiag, stride, y, y_stride, mu, n_valid, z, z_stride);
   GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_trsv_diag(Handle *h, long long ldw, long long w_off, int row0, const double *Wdiag, long long stride,
+                     const double *y, long long y_stride, const double *mu, int n_valid, const double *acc, double *z,
+                     long long z_stride, int batch) {
+  ProfScope ps__(h, PC_SOLVE);
+  trsv_diag_kernel<<<batch, 128, 0, h->stream>>>(ldw, w_off, row0, Wdiag, stride, y, y_stride, mu, n_valid, acc, z, z_stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_trsv_update(Handle *h, long long ld, long long l_off, int z_row0, int acc_row0, int ntiles, const double *L,
+                       long long stride, const double *z, double *acc, long long z_stride, int batch) {
+  if (ntiles <= 0) return 0;
+  ProfScope ps__(h, PC_SOLVE);
+  dim3 grid(ntiles, batch);
+  trsv_update_kernel<<<grid, 256, 0, h->stream>>>(ld, l_off, z_row0, acc_row0, L, stride, z, acc, z_stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_trsv_sweep(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
+                      long long y_stride, const double *mu, int n_valid, double *z, double *acc, long long z_stride,
+                      int batch) {
+  const int nt = np / TILE;
+  cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)z_stride * batch, h->stream);
+  if (e != cudaSuccess) return -1000;
+  for (int j = 0; j < nt; j++) {
+    const long long doff = (long long)j * TILE * (np + 1);
+    int rc = launch_trsv_diag(h, np, doff, j * TILE, Wdiag, stride, y, y_stride, mu, n_valid, acc, z, z_stride, batch);
+    if (rc) return rc;
+    rc = launch_trsv_update(h, np, doff + TILE, j * TILE, (j + 1) * TILE, nt - 1 - j, L, stride, z, acc, z_stride, batch);
+    if (rc) return rc;
+  }
   return 0;
 }
 

@@ -47,6 +47,10 @@ GPB200_API int gpb200_version(void);
 /* cap on the device workspace the batched entry points may allocate (bytes; 0 = 60% of free) */
 GPB200_API int gpb200_set_workspace_limit(gpb200_handle_t h, long long bytes);
 
+/* tuning/testing knob: Cholesky panel width in 128-column tiles (0 = automatic: pure left-looking
+ * for batches >= 64, 8-tile panels + right-looking trailing updates for small batches) */
+GPB200_API int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles);
+
 /* per-kernel-class timing with CUDA events on the handle's stream (used by bench.py for the
  * roofline of the dominant kernel).  Classes: 0 DMMA tile GEMM, 1 POTRF tile, 2 TRSM tile,
  * 3 Gram, 4 triangular mat-vec/solves, 5 other.  get_profile synchronises, sums and resets. */
@@ -151,6 +155,30 @@ GPB200_API int gpb200_gp_condition(gpb200_handle_t h, int n, int m, const double
  * the block layout the reference uses: sigma is (ng+nd)^2 with the GIVEN block first. */
 GPB200_API int gpb200_cond_mvn(gpb200_handle_t h, int ng, int nd, const double *mean, const double *sigma,
                     int lds, const double *x_given, double *cond_mean, double *cond_var, int ldv);
+
+/* ---- (e) multi-GPU block-cyclic Cholesky of ONE large matrix: per-rank building blocks ------------
+ * DEVICE pointers only.  A panel is a block column of the padded matrix (np = ceil(n/128)*128)
+ * stored compactly: rows [col0, np) x ncols columns, leading dimension ldp >= np - col0 (even);
+ * col0 and ncols are multiples of 128.  Panels are distributed block-column-cyclically over the
+ * GPUs of one box; the panel broadcast between these calls is an NCCL collective issued by the host
+ * side (gp_b200/block_cyclic.py, torch.distributed).  The reference has no counterpart:
+ * the semantics are those of cholesky_decompose / multi_normal_cholesky at sizes one GPU's time
+ * budget does not allow. */
+GPB200_API int gpb200_mg_gram_panel(gpb200_handle_t h, int n, const double *x, double alpha, double rho,
+                                    double diag_add, int col0, int ncols, double *P, long long ldp);
+/* Cholesky of the (already updated) panel in place: diagonal block + everything below it */
+GPB200_API int gpb200_mg_panel_factor(gpb200_handle_t h, int n, int col0, int ncols, double *P, long long ldp,
+                                      int *info_dev);
+/* right-looking update of a panel to the right: C -= P(rows of C) P(cols of C)^T, lower part */
+GPB200_API int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P,
+                                      long long ldp, int ccol0, int cncols, double *C, long long ldc);
+/* forward substitution through a factored panel: z[col0..] solved, acc[below] += L z;
+ * y, acc, z: length-np device vectors; wscratch: ldp x 128 doubles */
+GPB200_API int gpb200_mg_panel_trsv(gpb200_handle_t h, int n, int col0, int ncols, const double *P,
+                                    long long ldp, const double *y, double *acc, double *z, double *wscratch);
+/* out[0] += sum of log L_ii over the panel's diagonal (device scalar) */
+GPB200_API int gpb200_mg_panel_logdiag(gpb200_handle_t h, int n, int col0, int ncols, const double *P,
+                                       long long ldp, double *out);
 
 #ifdef __cplusplus
 }
