@@ -13,7 +13,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-SO = os.path.join(LIBDIR, "libgpb200.so")
+TAG = os.environ.get("GPB_BUILD_TAG", "")            # experiment builds: libgpb200_<tag>.so with extra -D flags
+SO = os.path.join(LIBDIR, "libgpb200%s.so" % ("_" + TAG if TAG else ""))
+EXTRA = os.environ.get("GPB_EXTRA_NVCC", "").split()
 SOURCES = ["gemm.cu", "panel.cu", "gram.cu", "solve.cu", "api.cu"]
 HEADERS = ["common.cuh", "gram.cuh", os.path.join("..", "..", "include", "gpb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -30,7 +32,7 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" + ("_" + TAG if TAG else ""))
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     jobs = []
@@ -42,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return job, r
 

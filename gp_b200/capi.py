@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgpb200.so")
+LIB_PATH = os.environ.get("GPB200_LIB", os.path.join(_HERE, "lib", "libgpb200.so"))
 
 KINDS = {"QQ": 0, "QR": 1, "RQ": 2, "RR": 3, "QT": 4, "TQ": 5, "RT": 6, "TR": 7, "TT": 8, "RR_QUIRK": 9}
 
@@ -48,11 +48,14 @@ SIGNATURES = {
     "gpb200_trsm_lower": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "gpb200_potrs": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "gpb200_trmv_lower": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "gpb200_trmv_lower_t": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "gpb200_mvn_chol_lpdf": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gpb200_lml_grad": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "gpb200_lml_grad_batched": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, _ll, C.c_void_p,
                                           C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpb200_rbf_cov_chol": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "gpb200_se_chol_tangent": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                         C.c_void_p, C.c_void_p]),
     "gpb200_approx_L": (C.c_int, [_h, C.c_int, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p), C.c_void_p]),
     "gpb200_approx_Lz": (C.c_int, [_h, C.c_int, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
@@ -257,6 +260,13 @@ class Handle:
         self._check(self.lib.gpb200_trmv_lower(self._h, n, _ptr(L), max(n, 1), _ptr(z), _ptr(f)), "trmv_lower")
         return f
 
+    def trmv_lower_t(self, L, z):
+        L = _f(L); z = np.ascontiguousarray(z, dtype=np.float64)
+        n = z.shape[0]
+        f = np.empty(n)
+        self._check(self.lib.gpb200_trmv_lower_t(self._h, n, _ptr(L), max(n, 1), _ptr(z), _ptr(f)), "trmv_lower_t")
+        return f
+
     def mvn_chol_lpdf(self, y, mu, L, drop_constants=False):
         L = _f(L); y = np.ascontiguousarray(y, dtype=np.float64)
         n = y.shape[0]
@@ -304,6 +314,15 @@ class Handle:
         n = x1.shape[0]
         L = np.empty((n, n), order="F"); dL = np.empty((n, n), order="F")
         self._check(self.lib.gpb200_rbf_cov_chol(self._h, n, _ptr(x1), l, _ptr(L), _ptr(dL)), "rbf_cov_chol")
+        return L, dL
+
+    def se_chol_tangent(self, x, alpha, rho, diag_add, wrt):
+        """L = chol(cov_exp_quad(x, alpha, rho) + diag_add I) and dL/d(alpha if wrt == 0 else rho)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        n = x.shape[0]
+        L = np.empty((n, n), order="F"); dL = np.empty((n, n), order="F")
+        self._check(self.lib.gpb200_se_chol_tangent(self._h, n, _ptr(x), alpha, rho, diag_add, int(wrt), _ptr(L),
+                                                    _ptr(dL)), "se_chol_tangent")
         return L, dL
 
     def _tables(self, Ls, dLdls):

@@ -678,6 +678,24 @@ extern "C" int gpb200_trmv_lower(gpb200_handle_t h, int n, const double *L, int 
   return finish(h);
 }
 
+extern "C" int gpb200_trmv_lower_t(gpb200_handle_t h, int n, const double *L, int ldl, const double *z, double *f) {
+  CHECK_H(h);
+  if (n < 0) BAD_ARG(h, 2, "trmv_lower_t: negative n");
+  if (ldl < std::max(1, n)) BAD_ARG(h, 4, "trmv_lower_t: ldl < n");
+  if (n == 0) return 0;
+  const int np = round_up(n, TILE);
+  Arena a;
+  RC(ws_reserve(h, 2 * pad256((size_t)np * np * 8) + 4 * pad256(np * 8), &a));
+  double *Lbuf = nullptr;
+  RC(stage_lower(h, a, n, np, L, ldl, &Lbuf));
+  double *dz = a.take<double>(np), *df = a.take<double>(np);
+  GPB_CUDA(h, cudaMemsetAsync(dz, 0, sizeof(double) * np, h->stream));
+  RC(to_device(h, z, dz, n));
+  RC(launch_trmv_lower_t(h, np, Lbuf, 0, dz, 0, df, 0, 1));
+  RC(from_device(h, df, f, n * sizeof(double)));
+  return finish(h);
+}
+
 extern "C" int gpb200_mvn_chol_lpdf(gpb200_handle_t h, int n, const double *y, const double *mu, const double *L,
                                     int ldl, int drop_constants, double *lp) {
   CHECK_H(h);
@@ -834,10 +852,10 @@ int tasks_tangent(Handle *h, int nt, TaskList *t1, TaskList *ta, TaskList *tl) {
 }
 }  // namespace
 
-extern "C" int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, double l, double *L, double *dLdl) {
-  CHECK_H(h);
-  if (n < 0) BAD_ARG(h, 2, "rbf_cov_chol: negative n");
-  if (n == 0) return 0;
+namespace {
+// L = chol(S), dL = L Phi(L^-1 Sdot L^-T) for the Gram/tangent pair selected by `mode`
+int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, double l, double dadd, int mode, double *L,
+                        double *dLdl) {
   const int np = round_up(n, TILE), nt = np / TILE;
   const size_t mat = (size_t)np * np;
   Arena a;
@@ -848,7 +866,7 @@ extern "C" int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, d
   double *stage = h->device_ptrs ? nullptr : a.take<double>((size_t)n * n);
   GPB_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int), h->stream));
   RC(to_device(h, x1, dx, n));
-  RC(launch_gram_rbf_tangent(h, n, np, dx, l, 1e-10, Lbuf, Dbuf));
+  RC(launch_gram_tangent(h, n, np, dx, alpha, l, dadd, mode, Lbuf, Dbuf));
   RC(chol_batched(h, Lbuf, np, (long long)mat, n, 1, info, nullptr));
   int hinfo = 0;
   RC(read_info(h, info, &hinfo));
@@ -884,6 +902,23 @@ extern "C" int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, d
   }
   RC(finish(h));
   return hinfo;
+}
+}  // namespace
+
+extern "C" int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, double l, double *L, double *dLdl) {
+  CHECK_H(h);
+  if (n < 0) BAD_ARG(h, 2, "rbf_cov_chol: negative n");
+  if (n == 0) return 0;
+  return chol_tangent_common(h, n, x1, 1.0, l, 1e-10, 0, L, dLdl);
+}
+
+extern "C" int gpb200_se_chol_tangent(gpb200_handle_t h, int n, const double *x, double alpha, double rho,
+                                      double diag_add, int wrt, double *L, double *dL) {
+  CHECK_H(h);
+  if (n < 0) BAD_ARG(h, 2, "se_chol_tangent: negative n");
+  if (wrt != 0 && wrt != 1) BAD_ARG(h, 7, "se_chol_tangent: wrt must be 0 (alpha) or 1 (rho)");
+  if (n == 0) return 0;
+  return chol_tangent_common(h, n, x, alpha, rho, diag_add, wrt == 1 ? 1 : 2, L, dL);
 }
 
 namespace {

@@ -142,16 +142,19 @@ __global__ void __launch_bounds__(256) gram_se_panel_kernel(int n, int np, const
   }
 }
 
-// ---- rbf_cov_chol Gram + tangent (covariance.cpp:15-25): padded, full square -------------------
-__global__ void __launch_bounds__(256) gram_rbf_tangent_kernel(int n, int np, const double *__restrict__ x, double l,
-                                                              double jitter, double *__restrict__ S,
-                                                              double *__restrict__ Sdot) {
+// ---- Gram + parameter tangent for the forward-mode Cholesky: padded, full square ----------------
+// mode 0: rbf_cov_chol literal (covariance.cpp:15-25): S = exp(-d^2/(2 l^2)) + jitter I, dS/dl
+// mode 1: cov_exp_quad form, tangent w.r.t. rho:   S = alpha^2 exp(-0.5 d^2/rho^2) + c I, dS/drho = S_se d^2/rho^3
+// mode 2: cov_exp_quad form, tangent w.r.t. alpha: dS/dalpha = 2 alpha exp(-0.5 d^2/rho^2)
+__global__ void __launch_bounds__(256) gram_tangent_kernel(int n, int np, const double *__restrict__ x, double alpha,
+                                                          double l, double dadd, int mode, double *__restrict__ S,
+                                                          double *__restrict__ Sdot) {
   __shared__ double xs[TILE], ys[TILE];
   const int r0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE, tid = threadIdx.x;
   if (tid < TILE) xs[tid] = (r0 + tid < n) ? x[r0 + tid] : 0.0;
   else ys[tid - TILE] = (c0 + tid - TILE < n) ? x[c0 + tid - TILE] : 0.0;
   __syncthreads();
-  const double two_l2 = 2.0 * l * l, l3 = l * l * l;
+  const double two_l2 = 2.0 * l * l, l3 = l * l * l, a2 = alpha * alpha, nh = -0.5 / (l * l);
   const int rl = 2 * (tid & 63), cq = tid >> 6;
   for (int s = 0; s < 32; s++) {
     const int cl = cq + 4 * s, j = c0 + cl;
@@ -161,9 +164,15 @@ __global__ void __launch_bounds__(256) gram_rbf_tangent_kernel(int n, int np, co
       const int i = r0 + rl + e;
       if (i < n && j < n) {
         const double d = xs[rl + e] - ys[cl];
-        const double ev = exp(-(d * d) / two_l2);
-        v[e] = ev + ((i == j) ? jitter : 0.0);
-        dv[e] = ev * d * d / l3;
+        if (mode == 0) {
+          const double ev = exp(-(d * d) / two_l2);
+          v[e] = ev + ((i == j) ? dadd : 0.0);
+          dv[e] = ev * d * d / l3;
+        } else {
+          const double ev = (i == j) ? 1.0 : exp(d * d * nh);
+          v[e] = a2 * ev + ((i == j) ? dadd : 0.0);
+          dv[e] = (mode == 1) ? a2 * ev * d * d / l3 : 2.0 * alpha * ev;
+        }
       } else {
         v[e] = (i == j) ? 1.0 : 0.0;
         dv[e] = 0.0;
@@ -260,11 +269,11 @@ int launch_gram_se_panel(Handle *h, int n, int np, const double *x, double alpha
   return 0;
 }
 
-int launch_gram_rbf_tangent(Handle *h, int n, int np, const double *x, double l, double jitter, double *S,
-                            double *Sdot) {
+int launch_gram_tangent(Handle *h, int n, int np, const double *x, double alpha, double l, double dadd, int mode,
+                        double *S, double *Sdot) {
   dim3 grid(np / TILE, np / TILE);
   ProfScope ps__(h, PC_GRAM);
-  gram_rbf_tangent_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, l, jitter, S, Sdot);
+  gram_tangent_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, alpha, l, dadd, mode, S, Sdot);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

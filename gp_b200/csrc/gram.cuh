@@ -12,8 +12,8 @@ int launch_gram_outer(Handle *h, int kind, int n, int m, const double *x, const 
                       double *K, long long ldk);
 int launch_gram_se_batched(Handle *h, int n, int np, const double *x, long long x_stride, const double *theta,
                            double jitter, int lower_only, double *K, long long stride, int batch);
-int launch_gram_rbf_tangent(Handle *h, int n, int np, const double *x, double l, double jitter, double *S,
-                            double *Sdot);
+int launch_gram_tangent(Handle *h, int n, int np, const double *x, double alpha, double l, double dadd, int mode,
+                        double *S, double *Sdot);
 int launch_gram_deriv(Handle *h, int n, int nblocks, const double *t, double alpha, double rho, const double *noise,
                       double jitter, int quirk, double *K, long long ldk);
 int launch_gram_ard(Handle *h, int n, int m, int D, const double *X, long long ldx, const double *Y, long long ldy,

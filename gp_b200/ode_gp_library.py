@@ -77,3 +77,57 @@ def sample_derivs(params, ynoise, ti, rng=None, handle=None):
     mu, cov = sample_derivs_moments(params, ynoise, ti, handle=h)
     L = h.potrf(cov)
     return mu + h.trmv_lower(L, rng.standard_normal(mu.shape[0]))
+
+
+def create_p_dotXnS(Xn_list, mn, Kn, theta, rng=None, handle=None):
+    """R/ode_gp_library.R:43-93: closure that, given a new state x*, returns the conditional normal
+    of the derivative there given the data and every derivative already drawn, then draws from it.
+
+    Differences from the R text, all of them benign: the pre-factorisation of K_XX + 1e-6 I is a GPU
+    Cholesky instead of qr() (:55-57); `rnorm(1, mean, condVar)` passes a VARIANCE as sd (:84,
+    SURVEY Appendix A.3) -- reproduced by default (sd_is_variance=True on the returned closure).
+    Returns the closure; each call returns {"mu", "sigma", "dot_xs"} like the reference (:91).
+    """
+    h = handle or capi.default_handle()
+    rng = rng or np.random.default_rng()
+    X = np.column_stack([np.asarray(c, dtype=np.float64) for c in Xn_list])
+    N, D = X.shape
+    mn = np.asarray(mn, dtype=np.float64)
+    Kn = np.asarray(Kn, dtype=np.float64)
+    K_XX = h.gram_ard(X, X, float(theta[0]), theta[1])
+    L = h.potrf(K_XX + 1e-6 * np.eye(N))
+    K_XX_1_mn = h.potrs(L, mn)
+    K_XX_1_Kn = h.potrs(L, Kn)
+    state = {"i": 1, "K_XsX": np.zeros((0, N)), "K_XsXs": np.zeros((0, 0)), "Xs": np.zeros((0, D)),
+             "dot_Xs": np.zeros(0)}
+
+    def p_dotXnS(xs_vec, sd_is_variance=True):
+        xs = np.asarray(xs_vec, dtype=np.float64).reshape(1, D)
+        st = state
+        st["K_XsX"] = np.vstack([st["K_XsX"], h.gram_ard(xs, X, float(theta[0]), theta[1])])
+        kss = h.gram_ard(xs, xs, float(theta[0]), theta[1])
+        if st["Xs"].shape[0]:
+            cross = h.gram_ard(st["Xs"], xs, float(theta[0]), theta[1])
+            st["K_XsXs"] = np.block([[st["K_XsXs"], cross], [cross.T, kss]])
+        else:
+            st["K_XsXs"] = kss
+        A = st["K_XsX"]
+        S = h.potrs(L, np.asfortranarray(A.T))            # solve(K_XX_qr, t(K_XsX))
+        m = A @ K_XX_1_mn
+        K = st["K_XsXs"] - A @ S + A @ K_XX_1_Kn @ S
+        K = (K + K.T) / 2 + 1e-6 * np.eye(K.shape[0])
+        i = st["i"]
+        if i == 1:
+            cmean, cvar = m[0], K[0, 0]
+        else:
+            # condMVN(m, K, i, 1:(i-1), c(dot_Xs)): last point given all earlier draws
+            cm, cv = h.cond_mvn(m, K, i - 1, st["dot_Xs"])
+            cmean, cvar = cm[0], cv[0, 0]
+        sd = cvar if sd_is_variance else np.sqrt(max(cvar, 0.0))
+        dot_xs = cmean + sd * rng.standard_normal()
+        st["i"] = i + 1
+        st["Xs"] = np.vstack([st["Xs"], xs])
+        st["dot_Xs"] = np.append(st["dot_Xs"], dot_xs)
+        return {"mu": float(cmean), "sigma": float(cvar), "dot_xs": float(dot_xs)}
+
+    return p_dotXnS

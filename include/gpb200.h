@@ -107,6 +107,9 @@ GPB200_API int gpb200_potrs(gpb200_handle_t h, int n, int nrhs, const double *L,
 /* f = L z, lower-triangular (exact_gp.stan:25, heteroscedastic.stan:31-32) */
 GPB200_API int gpb200_trmv_lower(gpb200_handle_t h, int n, const double *L, int ldl, const double *z,
                       double *f);
+/* f = L^T z: the adjoint of the above (zbar = L^T fbar in the reverse sweep of f = L z) */
+GPB200_API int gpb200_trmv_lower_t(gpb200_handle_t h, int n, const double *L, int ldl, const double *z,
+                        double *f);
 /* multi_normal_cholesky_lpdf(y | mu, L) (fit_hyperparameters.stan:31); mu may be NULL (zeros);
  * drop_constants != 0 omits -0.5 n log(2 pi) like Stan's `~` statement. */
 GPB200_API int gpb200_mvn_chol_lpdf(gpb200_handle_t h, int n, const double *y, const double *mu,
@@ -133,6 +136,13 @@ GPB200_API int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
  * upper triangle. */
 GPB200_API int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, double l, double *L,
                         double *dLdl);
+
+/* Generalisation used by the non-centred latent models (exact_gp.stan:17-25 alpha = 1, diag_add =
+ * 1e-10; fit_full_gp.stan:18-26; heteroscedastic.stan:23-32): L = chol(cov_exp_quad(x, alpha, rho) +
+ * diag_add I) and its forward-mode tangent dL/dalpha (wrt = 0) or dL/drho (wrt = 1).  With f = L z
+ * the reverse sweep through the Cholesky that Stan performs is  d lp/d theta = fbar^T (dL z). */
+GPB200_API int gpb200_se_chol_tangent(gpb200_handle_t h, int n, const double *x, double alpha, double rho,
+                                      double diag_add, int wrt, double *L, double *dL);
 
 /* approx_L (covariance.cpp:49-96): cubic-Hermite interpolation in l between tabulated factors;
  * Ls / dLdls are P pointers to n x n column-major tables, lp the P grid points. */

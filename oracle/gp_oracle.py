@@ -488,3 +488,69 @@ def lml_grad_lapack(x, y, alpha, rho, sigma, jitter=0.0):
     g_rho = 0.5 * alpha * alpha * s_d2 / rho ** 3
     g_sigma = sigma * (float(a @ a) - float(np.sum(kd)))
     return float(val), np.array([g_alpha, g_rho, g_sigma])
+
+
+# --------------------------------------------------------------------------------------------------
+# CS-E  non-centred latent exact GP (models/exact_gp.stan:16-33): lp and gradients, with the gradient
+# through the Cholesky taken by the REVERSE-mode adjoint (independent of the forward-mode route the
+# CUDA path uses):  Lbar = tril(fbar z^T), Kbar = L^-T Phi(L^T Lbar) L^-1 (symmetrised),
+# lbar = sum Kbar * dK/dl.
+# --------------------------------------------------------------------------------------------------
+def exact_gp_lp_grad(x, y, l, sigma, z, alpha=1.0, jitter=1e-10):
+    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64); z = np.asarray(z, dtype=np.float64)
+    n = x.shape[0]
+    Kse = cov_exp_quad(x, alpha, l)
+    L = cholesky_decompose(add_diag(Kse, jitter))
+    f = L @ z
+    r = y - f
+    lp = -0.5 * float(z @ z) + 3.0 * math.log(l) - 4.0 * l - n * math.log(sigma) - 0.5 * float(r @ r) / sigma ** 2
+    fbar = r / sigma ** 2
+    Lbar = np.tril(np.outer(fbar, z))
+    P = phi_lower(L.T @ Lbar)
+    # Kbar = L^-T P L^-1
+    T = sla.solve_triangular(L, P, lower=True, trans="T", check_finite=False)          # L^-T P
+    Kbar = sla.solve_triangular(L, T.T, lower=True, trans="T", check_finite=False).T   # (L^-T (L^-T P)^T)^T = L^-T P L^-1
+    Kbar = 0.5 * (Kbar + Kbar.T)
+    d = x[:, None] - x[None, :]
+    g_l = float(np.sum(Kbar * (Kse * d * d / l ** 3))) + 3.0 / l - 4.0
+    g_sigma = -n / sigma + float(r @ r) / sigma ** 3
+    g_z = -z + L.T @ fbar
+    return lp, {"l": g_l, "sigma": g_sigma, "z": g_z, "f": f}
+
+
+def create_p_dotXnS(Xn_list, mn, Kn, theta, normals, sd_is_variance=True):
+    """R/ode_gp_library.R:43-93 with the random normals supplied by the caller (one per call)."""
+    X = np.column_stack([np.asarray(c, dtype=np.float64) for c in Xn_list])
+    N, D = X.shape
+    K_XX = rk_QQard(X, X, theta) + 1e-6 * np.eye(N)
+    K_XX_1_mn = np.linalg.solve(K_XX, mn)
+    K_XX_1_Kn = np.linalg.solve(K_XX, Kn)
+    st = {"i": 1, "A": np.zeros((0, N)), "Kss": np.zeros((0, 0)), "Xs": np.zeros((0, D)), "d": np.zeros(0)}
+    it = iter(normals)
+
+    def call(xs_vec):
+        xs = np.asarray(xs_vec, dtype=np.float64).reshape(1, D)
+        st["A"] = np.vstack([st["A"], rk_QQard(xs, X, theta)])
+        kss = rk_QQard(xs, xs, theta)
+        if st["Xs"].shape[0]:
+            cross = rk_QQard(st["Xs"], xs, theta)
+            st["Kss"] = np.block([[st["Kss"], cross], [cross.T, kss]])
+        else:
+            st["Kss"] = kss
+        A = st["A"]
+        S = np.linalg.solve(K_XX, A.T)
+        m = A @ K_XX_1_mn
+        K = st["Kss"] - A @ S + A @ K_XX_1_Kn @ S
+        K = (K + K.T) / 2 + 1e-6 * np.eye(K.shape[0])
+        i = st["i"]
+        if i == 1:
+            cmean, cvar = m[0], K[0, 0]
+        else:
+            cm, cv = condMVN(m, K, [i - 1], list(range(i - 1)), st["d"])
+            cmean, cvar = cm[0], cv[0, 0]
+        sd = cvar if sd_is_variance else math.sqrt(max(cvar, 0.0))
+        dot_xs = cmean + sd * next(it)
+        st["i"] = i + 1
+        st["Xs"] = np.vstack([st["Xs"], xs]); st["d"] = np.append(st["d"], dot_xs)
+        return {"mu": float(cmean), "sigma": float(cvar), "dot_xs": float(dot_xs)}
+    return call

@@ -1,0 +1,88 @@
+"""BASELINE.json configs at their full sizes on the GPU: oracle comparison on a
+sample of the items plus size-independent properties on all of them."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as o
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_c1_latent_form_backward_error(handle):
+    # C1 latent form: x = seq(0, 10, length = 100), jitter 1e-10 (exact_gp.stan:17-23): cond ~ 1e10
+    x = np.linspace(0, 10, 100)
+    K = o.gram_se(x, 1.0, 1.0, 1e-10)
+    L = handle.potrf(K)
+    assert np.linalg.norm(L @ L.T - K) / np.linalg.norm(K) < 20 * 100 * EPS
+
+
+def test_c2_joint_derivative_covariance_n512(handle):
+    # C2: t = linspace(0, 10, 512), (y, y', y'') joint covariance 1536^2 + diag noise + 1e-6
+    t = np.linspace(0, 10, 512)
+    alpha, rho, noise = 1.0, 1.3, [0.1, 0.2, 0.4]
+    K = handle.gram_deriv(t, alpha, rho, noise, 1e-6, nblocks=3)
+    Kr = o.gram_deriv(t, alpha, rho, noise, 1e-6, nblocks=3)
+    assert K.shape == (1536, 1536) and relerr(K, Kr) < 1e-13
+    L = handle.potrf(K)
+    assert np.linalg.norm(L @ L.T - K) / np.linalg.norm(K) < 20 * 1536 * EPS
+    assert relerr(L, o.cholesky_decompose(Kr)) < 1e-8
+    # pendulum-like data: y, y', y'' of sin(t); LML of the joint observation vector
+    rng = np.random.default_rng(2)
+    yy = np.concatenate([np.sin(t), np.cos(t), -np.sin(t)]) + np.repeat(noise, 512) * rng.standard_normal(1536)
+    lp = handle.mvn_chol_lpdf(yy, None, L)
+    ref = o.multi_normal_cholesky_lpdf(yy, 0.0, o.cholesky_decompose(Kr))
+    assert abs(lp - ref) <= 1e-9 * abs(ref)
+    # 2-block p_dotXn form (1024^2) conditioned through the C ABI
+    K2 = handle.gram_deriv(t, alpha, rho, [0.1, 0.0], 1e-6, nblocks=2, quirk=True)
+    cm, cv = handle.cond_mvn(np.zeros(1024), K2, 512, np.sin(t))
+    rm, rv = o.p_dotXn(t, np.sin(t), (alpha, rho), 0.1)
+    assert relerr(cm, rm) < 1e-7 and relerr(cv, rv) < 1e-7
+    assert np.max(np.abs(cm[20:-20] - np.cos(t[20:-20]))) < 0.05   # derivative of sin is cos
+
+
+def test_c3_draws_n2048(handle):
+    # C3: N = 2048, one shared (x, y), theta draws (seed 3); here 24 draws, 4 checked against the oracle
+    n, B = 2048, 24
+    x, y = o.synth_xy(n, 3)
+    th = o.synth_theta(B, 3)
+    lml, grad, info = handle.lml_grad_batched(x, y, th)
+    assert np.all(info == 0) and np.all(np.isfinite(lml)) and np.all(np.isfinite(grad))
+    for b in (0, 7, 13, 23):
+        rv, rg = o.lml_grad_lapack(x, y, *th[b])
+        assert abs(lml[b] - rv) <= 1e-9 * abs(rv)
+        assert relerr(grad[b], rg) < 1e-9
+    # batching must not change a single bit of any item
+    lml1, grad1, _ = handle.lml_grad_batched(x, y, th[5:6])
+    assert lml1[0] == lml[5] and np.array_equal(grad1[0], grad[5])
+
+
+def test_c4_groups_n1024(handle):
+    # C4: independent per-group GPs (multiple_players): own (x_g, y_g, theta_g), N = 1024; 16 groups here
+    G, n = 16, 1024
+    xs, ys = zip(*[o.synth_xy(n, 4 + g) for g in range(G)])
+    X = np.stack(xs); Y = np.stack(ys)
+    th = o.synth_theta(G, 4)
+    lml, grad, info = handle.lml_grad_batched(X, Y, th)
+    assert np.all(info == 0)
+    for g in (0, 5, 15):
+        rv, rg = o.lml_grad_lapack(X[g], Y[g], *th[g])
+        assert abs(lml[g] - rv) <= 1e-9 * abs(rv) and relerr(grad[g], rg) < 1e-9
+    # permuting the groups permutes the results exactly
+    perm = np.random.default_rng(0).permutation(G)
+    lml_p, grad_p, _ = handle.lml_grad_batched(X[perm], Y[perm], th[perm])
+    assert np.array_equal(lml_p, lml[perm]) and np.array_equal(grad_p, grad[perm])
+
+
+def test_headline_n4096_sample(handle):
+    n, B = 4096, 3
+    x, y = o.synth_xy(n, 5)
+    th = o.synth_theta(B, 5)
+    lml, grad, info = handle.lml_grad_batched(x, y, th)
+    rv, rg = o.lml_grad_lapack(x, y, *th[1])
+    assert abs(lml[1] - rv) <= 1e-9 * abs(rv) and relerr(grad[1], rg) < 1e-9

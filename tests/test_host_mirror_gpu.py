@@ -102,3 +102,57 @@ def test_stan_math_mirror(handle):
         up[k] += 1e-6; um[k] -= 1e-6
         fd = (o.lp_fit_hyperparameters(x, y, *up) - o.lp_fit_hyperparameters(x, y, *um)) / 2e-6
         assert abs(fd - g[k]) < 1e-5 * max(1.0, abs(g[k]))
+
+
+def test_latent_exact_gp_gradient_through_cholesky(handle):
+    # CS-E, models/exact_gp.stan: the CUDA path takes the gradient through the Cholesky with the
+    # forward-mode tangent; the oracle with the reverse-mode adjoint -- they must agree
+    from gp_b200 import latent_gp
+    rng = np.random.default_rng(0)
+    n = 200
+    x = np.arange(n) * 0.8 + 0.05 * rng.standard_normal(n)
+    y = np.sin(x) + 0.1 * rng.standard_normal(n)
+    z = rng.standard_normal(n)
+    lp, g = latent_gp.exact_gp_log_prob(x, y, 0.9, 0.3, z, handle=handle)
+    rlp, rg = o.exact_gp_lp_grad(x, y, 0.9, 0.3, z)
+    assert abs(lp - rlp) <= 1e-9 * abs(rlp)
+    assert abs(g["l"] - rg["l"]) <= 1e-8 * abs(rg["l"])
+    assert abs(g["sigma"] - rg["sigma"]) <= 1e-9 * abs(rg["sigma"])
+    assert relerr(g["z"], rg["z"]) < 1e-9 and relerr(g["f"], rg["f"]) < 1e-9
+    # amplitude variant (fit_full_gp.stan) and the alpha tangent
+    L, dLa = handle.se_chol_tangent(x, 1.3, 0.9, 1e-6, 0)
+    hh = 1e-6
+    Lp = o.cholesky_decompose(o.gram_se(x, 1.3 + hh, 0.9, 1e-6)); Lm = o.cholesky_decompose(o.gram_se(x, 1.3 - hh, 0.9, 1e-6))
+    assert relerr(dLa, (Lp - Lm) / (2 * hh)) < 1e-6
+    assert relerr(L, o.cholesky_decompose(o.gram_se(x, 1.3, 0.9, 1e-6))) < 1e-9
+
+
+def test_create_p_dotXnS_sequential_sampler(handle):
+    # R/tests.R:78-99 shape: condition on data, then query new states one at a time
+    from gp_b200 import ode_gp_library as lib
+    tn = np.arange(-2, 2.0001, 0.4)
+    Xn = np.exp(tn)
+    # alpha = 1: with any other amplitude the R/kernels.R:31 quirk makes Kn indefinite (eig -0.8 here) and
+    # the reference's LU-based condMVN silently returns negative variances; the Cholesky-based GPU path
+    # raises NotPositiveDefiniteError instead (checked below)
+    theta = (1.0, [1.0])
+    mn, Kn = o.p_dotXn_solve(tn, Xn, (1.0, 1.0), 0.1)
+    normals = np.random.default_rng(3).standard_normal(6)
+
+    class FixedRng:
+        def __init__(self, v): self.v = list(v)
+        def standard_normal(self): return self.v.pop(0)
+
+    f = lib.create_p_dotXnS([Xn], mn, Kn, theta, rng=FixedRng(normals), handle=handle)
+    fr = o.create_p_dotXnS([Xn], mn, Kn, theta, normals)
+    for xs in (0.3, 0.9, 1.7, 2.5, 0.5, 4.0):
+        a, b = f([xs]), fr([xs])
+        assert abs(a["mu"] - b["mu"]) <= 1e-6 * max(1.0, abs(b["mu"]))
+        assert abs(a["sigma"] - b["sigma"]) <= 1e-6 * max(1e-6, abs(b["sigma"]))
+    from gp_b200 import NotPositiveDefiniteError
+    mn_q, Kn_q = o.p_dotXn_solve(tn, Xn, (1.2, 1.0), 0.1)       # quirk-affected, indefinite Kn
+    fq = lib.create_p_dotXnS([Xn], mn_q, Kn_q, (1.2, [1.0]), rng=FixedRng(normals), handle=handle)
+    fq([0.3])
+    with pytest.raises(NotPositiveDefiniteError):
+        for xs in (0.9, 1.7, 2.5):
+            fq([xs])

@@ -149,3 +149,15 @@ def test_lapack_route_matches_plain_route():
         v, g = o.lml_grad(x, y, *th)
         v2, g2 = o.lml_grad_lapack(x, y, *th)
         assert abs(v - v2) < 1e-12 * abs(v) and relerr(g2, g) < 1e-11
+
+
+def test_latent_gp_reverse_mode_adjoint_matches_finite_differences():
+    rng = np.random.default_rng(0)
+    x = np.arange(30) * 0.8
+    y = np.sin(x) + 0.1 * rng.standard_normal(30)
+    z = rng.standard_normal(30)
+    lp, g = o.exact_gp_lp_grad(x, y, 0.9, 0.3, z)
+    h = 1e-6
+    fd_l = (o.exact_gp_lp_grad(x, y, 0.9 + h, 0.3, z)[0] - o.exact_gp_lp_grad(x, y, 0.9 - h, 0.3, z)[0]) / (2 * h)
+    fd_s = (o.exact_gp_lp_grad(x, y, 0.9, 0.3 + h, z)[0] - o.exact_gp_lp_grad(x, y, 0.9, 0.3 - h, z)[0]) / (2 * h)
+    assert abs(fd_l - g["l"]) < 1e-6 * abs(g["l"]) and abs(fd_s - g["sigma"]) < 1e-6 * abs(g["sigma"])
