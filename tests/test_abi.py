@@ -35,9 +35,15 @@ def test_sass_is_sm100a_dmma():
     from gp_b200 import capi
     out = subprocess.check_output(["cuobjdump", "-lelf", capi.LIB_PATH], text=True)
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
-    sass = subprocess.check_output(["cuobjdump", "-sass", "-fun", "_ZN3gpb16gemm_tile_kernelILb0ELb0ELi0EEEvNS_10GemmParamsE",
-                                    capi.LIB_PATH], text=True)
-    assert sass.count("DMMA.8x8x4") >= 128 and "LDGSTS" in sass
+    sass = subprocess.check_output(["cuobjdump", "-sass", capi.LIB_PATH], text=True)
+    # split per function and look at the NT instance of the tile GEMM
+    chunks = sass.split("Function : ")
+    gemm = [c for c in chunks if c.startswith("_ZN3gpb16gemm_tile_kernelILb0ELb0ELi0E")]
+    assert len(gemm) == 1
+    assert gemm[0].count("DMMA.8x8x4") >= 128 and "LDGSTS" in gemm[0]
+    # no library GEMM/solver is linked: the O(N^3) work is ours
+    ldd = subprocess.check_output(["ldd", capi.LIB_PATH], text=True)
+    assert "cublas" not in ldd and "cusolver" not in ldd
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback():
