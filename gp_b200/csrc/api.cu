@@ -397,6 +397,15 @@ extern "C" int gpb200_set_profiling(gpb200_handle_t h, int on) {
   h->profiling = on ? 1 : 0;
   h->prof.clear();
   h->ev_used = 0;
+  if (on && h->ev_pool.size() < 1024) {
+    // create the event pool up front: cudaEventCreate inside a timed region costs host time
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1000;
+    while (h->ev_pool.size() < 1024) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return -1000;
+      h->ev_pool.push_back(e);
+    }
+  }
   return 0;
 }
 
@@ -746,15 +755,22 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
   RC(tasks_lauum(h, nt, &tl));
   const int ntasks = tl.count(0);
 
-  // chunk the batch so that the resident set fits the workspace limit
-  size_t freeb = 0, totalb = 0;
-  GPB_CUDA(h, cudaMemGetInfo(&freeb, &totalb));
-  size_t limit = h->ws_limit > 0 ? (size_t)h->ws_limit : (size_t)((freeb + h->ws_bytes) * 0.85);
-  const size_t per_item = pad256(mat * 8) * (want_grad ? 2 : 2) + 3 * pad256(np * 8) + pad256((size_t)ntasks * 32) + 64;
+  // chunk the batch so that the resident set fits the workspace limit.  cudaMemGetInfo costs
+  // milliseconds with tens of GB allocated, so it is only consulted when the workspace must grow.
+  const size_t per_item = pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)ntasks * 32) + 64;
   const size_t fixed = pad256((size_t)B * (x_stride ? n : 0) * 8 + n * 8) + pad256((size_t)B * (y_stride ? n : 0) * 8 + n * 8) +
                        pad256((size_t)B * 24) + pad256((size_t)B * 8) + pad256((size_t)B * 24) + pad256((size_t)B * 4) + 4096;
-  if (limit < fixed + per_item) BAD_ARG(h, 1002, "lml_grad_batched: workspace limit too small for one item");
-  int Bc = (int)std::min<size_t>((size_t)B, (limit - fixed) / per_item);
+  int Bc = B;
+  if (h->ws_limit > 0 || fixed + per_item * (size_t)B + 8192 > h->ws_bytes) {
+    size_t limit = (size_t)h->ws_limit;
+    if (h->ws_limit <= 0) {
+      size_t freeb = 0, totalb = 0;
+      GPB_CUDA(h, cudaMemGetInfo(&freeb, &totalb));
+      limit = (size_t)((freeb + h->ws_bytes) * 0.85);
+    }
+    if (limit < fixed + per_item + 8192) BAD_ARG(h, 1002, "lml_grad_batched: workspace limit too small for one item");
+    Bc = (int)std::min<size_t>((size_t)B, (limit - fixed - 8192) / per_item);
+  }
   Arena a;
   RC(ws_reserve(h, fixed + per_item * (size_t)Bc + 8192, &a));
 

@@ -17,37 +17,16 @@
 //   NN  T = L21 W11, W21 = -W22 T   recursive triangular inverse (K^-1 for the gradient)
 //   TN  G = W^T W  + fused trace epilogue  0.5 tr((a a^T - K^-1) dK/dtheta)  (the reverse sweep
 //                               of multi_normal_cholesky -> cholesky_decompose -> cov_exp_quad)
-#include <algorithm>
-
 #include "common.cuh"
 
 namespace gpb {
 
-#ifndef GPB_KC
-#define GPB_KC 16
-#endif
-#ifndef GPB_STAGES
-#define GPB_STAGES 4
-#endif
-constexpr int KC = GPB_KC;          // k-chunk per pipeline stage
-constexpr int STAGES = GPB_STAGES;  // cp.async stages in flight
-#ifndef GPB_WARPS_M
-#define GPB_WARPS_M 2
-#endif
-#ifndef GPB_WARPS_N
-#define GPB_WARPS_N 4
-#endif
-constexpr int WARPS_M = GPB_WARPS_M, WARPS_N = GPB_WARPS_N;   // warp grid over the 128x128 CTA tile
-constexpr int WM = TILE / WARPS_M, WN = TILE / WARPS_N;       // warp tile
-constexpr int MI = WM / 8, NI = WN / 8;                       // 8x8 mma tiles per warp
-constexpr int NTHREADS = 32 * WARPS_M * WARPS_N;
+constexpr int KC = 16;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;
 constexpr int LD_MC = TILE + 4;  // operand with the tile index contiguous: stage[KC][132]
-constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][KC+4]
-constexpr int STAGE_DOUBLES = (TILE * LD_KC > KC * LD_MC) ? TILE * LD_KC : KC * LD_MC;
-constexpr int CPR_K = KC / 2;                       // 16-byte chunks per row of a k-contiguous stage
-constexpr int ROWS_PER_R_K = NTHREADS / CPR_K;      // rows covered by one sweep of the CTA (k-contiguous)
-constexpr int NCOPY = KC * TILE / 2 / NTHREADS;     // 16-byte copies per thread per operand per stage
-static_assert(LD_KC % 16 == 4 && LD_MC % 16 == 4, "conflict-free fragment loads need ld == 4 mod 16");
+constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
+constexpr int STAGE_DOUBLES = TILE * LD_KC;  // 2560 >= KC * LD_MC = 2112
 constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * (int)sizeof(double);  // 163840
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -64,253 +43,224 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
-// scratch of the trace epilogue lives behind the pipeline stages so that the next tile's prefetch can
-// already be in flight while the epilogue of the current tile runs
-constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 3 * (NTHREADS / 32) + 8;
-constexpr int GEMM_SMEM_TOTAL = GEMM_SMEM_BYTES + EPI_SCRATCH_DOUBLES * (int)sizeof(double);
-
 template <bool A_KC, bool B_KC, int EPI>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams p, const long long total_work) {
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams p) {
   extern __shared__ __align__(16) double smem[];
+  const TileTask task = p.tasks[blockIdx.x];
+  const long long b = blockIdx.y;
+  const double *__restrict__ A = p.A.p + b * p.A.stride;
+  const double *__restrict__ Bm = p.B.p + b * p.B.stride;
   const long long lda = p.A.ld, ldb = p.B.ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = (warp % WARPS_M) * WM, wn = (warp / WARPS_M) * WN;
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
 
-  // per-thread copy geometry (identical for every tile): 4 x 16B for A and for B per stage; the r-th
-  // copy of a thread is `rstep` further along the operand's non-contiguous dimension
-  int dstA[NCOPY], dstB[NCOPY];
-  long long thrA, thrB;  // this thread's element offset inside an operand tile chunk
-  {
-    if (!A_KC) { const int k = tid >> 6, m2 = tid & 63; thrA = 2 * m2 + (long long)k * lda; }
-    else { const int m = tid / CPR_K, k2 = tid % CPR_K; thrA = 2 * k2 + (long long)m * lda; }
-    if (!B_KC) { const int k = tid >> 6, n2 = tid & 63; thrB = 2 * n2 + (long long)k * ldb; }
-    else { const int n = tid / CPR_K, k2 = tid % CPR_K; thrB = 2 * k2 + (long long)n * ldb; }
+  double acc[4][8][2];
 #pragma unroll
-    for (int r = 0; r < NCOPY; r++) {
-      const int idx = tid + NTHREADS * r;
-      dstA[r] = A_KC ? (idx / CPR_K) * LD_KC + 2 * (idx % CPR_K) : (idx >> 6) * LD_MC + 2 * (idx & 63);
-      dstB[r] = B_KC ? (idx / CPR_K) * LD_KC + 2 * (idx % CPR_K) : (idx >> 6) * LD_MC + 2 * (idx & 63);
+  for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) acc[ni][mi][0] = acc[ni][mi][1] = 0.0;
+
+  const int nk = task.k_len / KC;
+
+  // per-thread copy descriptors: 4 x 16B for A and 4 x 16B for B per stage
+  const double *srcA[4], *srcB[4];
+  int dstA[4], dstB[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int idx = tid + NTHREADS * r;
+    if (!A_KC) {
+      const int k = idx >> 6, m2 = idx & 63;
+      srcA[r] = A + (task.a_r + 2 * m2) + (long long)(task.a_c + k) * lda;
+      dstA[r] = k * LD_MC + 2 * m2;
+    } else {
+      const int m = idx >> 3, k2 = idx & 7;
+      srcA[r] = A + (task.a_r + 2 * k2) + (long long)(task.a_c + m) * lda;
+      dstA[r] = m * LD_KC + 2 * k2;
+    }
+    if (!B_KC) {
+      const int k = idx >> 6, n2 = idx & 63;
+      srcB[r] = Bm + (task.b_r + 2 * n2) + (long long)(task.b_c + k) * ldb;
+      dstB[r] = k * LD_MC + 2 * n2;
+    } else {
+      const int n = idx >> 3, k2 = idx & 7;
+      srcB[r] = Bm + (task.b_r + 2 * k2) + (long long)(task.b_c + n) * ldb;
+      dstB[r] = n * LD_KC + 2 * k2;
     }
   }
-  const long long rstepA = (A_KC ? ROWS_PER_R_K : NTHREADS / 64) * lda, rstepB = (B_KC ? ROWS_PER_R_K : NTHREADS / 64) * ldb;
   const long long stepA = A_KC ? (long long)KC : (long long)KC * lda;
   const long long stepB = B_KC ? (long long)KC : (long long)KC * ldb;
 
-  // state of the tile being computed / prefetched
-  const double *srcA = nullptr, *srcB = nullptr;
-  auto setup = [&](long long w, TileTask &task, long long &b) {
-    task = p.tasks[w % p.ntasks];
-    b = w / p.ntasks;
-    srcA = p.A.p + b * p.A.stride + task.a_r + (long long)task.a_c * lda + thrA;
-    srcB = p.B.p + b * p.B.stride + task.b_r + (long long)task.b_c * ldb + thrB;
-  };
-  // source addresses are recomputed from constant bases for every chunk: incrementing registers an
-  // in-flight LDGSTS still reads costs a long-scoreboard (WAR) stall per chunk
+  // The source addresses are recomputed from constant bases for every chunk: incrementing the
+  // registers an in-flight LDGSTS still reads costs a long-scoreboard (WAR) stall per chunk.
   auto load_stage = [&](int stage, int chunk) {
     double *sA = smem + stage * 2 * STAGE_DOUBLES;
     double *sB = sA + STAGE_DOUBLES;
-    const double *a0 = srcA + (long long)chunk * stepA, *b0 = srcB + (long long)chunk * stepB;
+    const long long offA = (long long)chunk * stepA, offB = (long long)chunk * stepB;
 #pragma unroll
-    for (int r = 0; r < NCOPY; r++) cp_async16(sA + dstA[r], a0 + r * rstepA);
+    for (int r = 0; r < 4; r++) cp_async16(sA + dstA[r], srcA[r] + offA);
 #pragma unroll
-    for (int r = 0; r < NCOPY; r++) cp_async16(sB + dstB[r], b0 + r * rstepB);
+    for (int r = 0; r < 4; r++) cp_async16(sB + dstB[r], srcB[r] + offB);
   };
-  auto load_frags = [&](const double *sA, const double *sB, int kk, double (&af)[MI], double (&bf)[NI]) {
+  auto load_frags = [&](const double *sA, const double *sB, int kk, double (&af)[8], double (&bf)[4]) {
 #pragma unroll
-    for (int mi = 0; mi < MI; mi++)
+    for (int mi = 0; mi < 8; mi++)
       af[mi] = A_KC ? sA[(wm + mi * 8 + g) * LD_KC + kk * 4 + t] : sA[(kk * 4 + t) * LD_MC + wm + mi * 8 + g];
 #pragma unroll
-    for (int ni = 0; ni < NI; ni++)
+    for (int ni = 0; ni < 4; ni++)
       bf[ni] = B_KC ? sB[(wn + ni * 8 + g) * LD_KC + kk * 4 + t] : sB[(kk * 4 + t) * LD_MC + wn + ni * 8 + g];
   };
-  auto prologue = [&](int nk) {  // all STAGES stages in flight
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) {
-      if (s < nk) load_stage(s, s);
-      cp_async_commit();
-    }
-  };
 
-  long long w = blockIdx.x;
-  if (w >= total_work) return;
-  TileTask task;
-  long long b;
-  setup(w, task, b);
-  prologue(task.k_len / KC);
+  // prologue: all STAGES stages in flight, wait for chunk 0, first fragments in registers
+#pragma unroll
+  for (int s = 0; s < STAGES; s++) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+  cp_async_wait<STAGES - 1>();
+  __syncthreads();
+  double af[2][8], bf[2][4];
+  load_frags(smem, smem + STAGE_DOUBLES, 0, af[0], bf[0]);
 
-  double acc[NI][MI][2];
-  while (true) {
-    const int nk = task.k_len / KC;
+  for (int kc = 0; kc < nk; kc++) {
+    const double *sA = smem + (kc % STAGES) * 2 * STAGE_DOUBLES;
+    const double *sB = sA + STAGE_DOUBLES;
 #pragma unroll
-    for (int ni = 0; ni < NI; ni++)
-#pragma unroll
-      for (int mi = 0; mi < MI; mi++) acc[ni][mi][0] = acc[ni][mi][1] = 0.0;
-
-    cp_async_wait<STAGES - 1>();
-    __syncthreads();
-    double af[2][MI], bf[2][NI];
-    load_frags(smem, smem + STAGE_DOUBLES, 0, af[0], bf[0]);
-
-    for (int kc = 0; kc < nk; kc++) {
-      const double *sA = smem + (kc % STAGES) * 2 * STAGE_DOUBLES;
-      const double *sB = sA + STAGE_DOUBLES;
-#pragma unroll
-      for (int kk = 0; kk < KC / 4; kk++) {
-        const int cur = kk & 1, nxt = cur ^ 1;
-        if (kk < KC / 4 - 1) {
-          load_frags(sA, sB, kk + 1, af[nxt], bf[nxt]);
-        } else {
-          // chunk transition, hidden behind the DMMAs of this last k-step: everybody has finished
-          // reading stage kc (its last fragments are in registers), chunk kc+1 has landed
-          cp_async_wait<STAGES - 2>();
-          __syncthreads();
-          if (kc + STAGES < nk) load_stage(kc % STAGES, kc + STAGES);
-          cp_async_commit();
-          if (kc + 1 < nk) {
-            const double *nA = smem + ((kc + 1) % STAGES) * 2 * STAGE_DOUBLES;
-            load_frags(nA, nA + STAGE_DOUBLES, 0, af[nxt], bf[nxt]);
-          }
-        }
-#pragma unroll
-        for (int ni = 0; ni < NI; ni++)
-#pragma unroll
-          for (int mi = 0; mi < MI; mi++) dmma884(acc[ni][mi], bf[cur][ni], af[cur][mi]);
-      }
-    }
-
-    // ---- tile boundary: every stage is free (the barrier of the last transition ordered all reads
-    // of this tile's data); start the next tile's loads, then run this tile's epilogue under them
-    const TileTask cur_task = task;
-    const long long cur_b = b;
-    w += gridDim.x;
-    const bool more = w < total_work;
-    if (more) {
-      setup(w, task, b);
-      prologue(task.k_len / KC);
-    }
-
-    if (EPI == EPI_AXPBY) {
-      double *__restrict__ C = p.C.p + cur_b * p.C.stride;
-      const double *__restrict__ C0 = p.C0.p ? p.C0.p + cur_b * p.C0.stride : nullptr;
-      const double alpha = p.alpha, beta = p.beta;
-#pragma unroll
-      for (int ni = 0; ni < NI; ni++) {
-        const int n = cur_task.c_c + wn + ni * 8 + g;
-#pragma unroll
-        for (int mi = 0; mi < MI; mi++) {
-          const int m = cur_task.c_r + wm + mi * 8 + 2 * t;
-          double2 v = make_double2(alpha * acc[ni][mi][0], alpha * acc[ni][mi][1]);
-          if (C0) {
-            const double2 c0 = *reinterpret_cast<const double2 *>(C0 + m + (long long)n * p.C0.ld);
-            v.x = fma(beta, c0.x, v.x);
-            v.y = fma(beta, c0.y, v.y);
-          }
-          *reinterpret_cast<double2 *>(C + m + (long long)n * p.C.ld) = v;
+    for (int kk = 0; kk < KC / 4; kk++) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk < KC / 4 - 1) {
+        load_frags(sA, sB, kk + 1, af[nxt], bf[nxt]);
+      } else {
+        // Chunk transition, hidden behind the DMMAs of this last k-step: everybody has finished
+        // reading stage kc (its last fragments are in registers), chunk kc+1 has landed.
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kc + STAGES < nk) load_stage(kc % STAGES, kc + STAGES);
+        cp_async_commit();
+        if (kc + 1 < nk) {
+          const double *nA = smem + ((kc + 1) % STAGES) * 2 * STAGE_DOUBLES;
+          load_frags(nA, nA + STAGE_DOUBLES, 0, af[nxt], bf[nxt]);
         }
       }
-    } else {
-      // ---- fused trace epilogue: this tile of G = K^-1 never has to reach HBM ---------------
-      double *scr = smem + STAGES * 2 * STAGE_DOUBLES;
-      double *xr = scr, *xc = scr + TILE, *ar = scr + 2 * TILE, *ac = scr + 3 * TILE;
-      double *red = scr + 4 * TILE;
-      const double *x = p.x + cur_b * p.x_stride;
-      const double *av = p.avec + cur_b * p.a_stride;
-      __syncthreads();  // the previous tile's readers of the scratch are done
-      if (tid < TILE) {
-        const int i = cur_task.c_r + tid;
-        xr[tid] = (i < p.n) ? x[i] : 0.0;
-        ar[tid] = (i < p.n) ? av[i] : 0.0;
-      } else if (tid < 2 * TILE) {
-        const int j = cur_task.c_c + tid - TILE;
-        xc[tid - TILE] = (j < p.n) ? x[j] : 0.0;
-        ac[tid - TILE] = (j < p.n) ? av[j] : 0.0;
-      }
-      __syncthreads();
-      const double rho = p.theta[cur_b * 3 + 1];
-      const double nh = -0.5 / (rho * rho);
-      const bool diag_tile = (cur_task.flags & 1) != 0;
-      double s_se = 0.0, s_d2 = 0.0, s_tr = 0.0;
-      double *__restrict__ C = p.C.p ? p.C.p + cur_b * p.C.stride : nullptr;
 #pragma unroll
-      for (int ni = 0; ni < NI; ni++) {
-        const int nl = wn + ni * 8 + g;
-        const int j = cur_task.c_c + nl;
+      for (int ni = 0; ni < 4; ni++)
 #pragma unroll
-        for (int mi = 0; mi < MI; mi++) {
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int ml = wm + mi * 8 + 2 * t + e;
-            const int i = cur_task.c_r + ml;
-            const double G = acc[ni][mi][e];
-            if (i < p.n && j < p.n) {
-              const double d = xr[ml] - xc[nl];
-              const double d2 = d * d;
-              const double ek = exp(d2 * nh);
-              const double M = ar[ml] * ac[nl] - G;
-              s_se += M * ek;
-              s_d2 += M * ek * d2;
-              if (diag_tile && i == j) s_tr += G;
-            }
-          }
-          if (C) {
-            const int m = cur_task.c_r + wm + mi * 8 + 2 * t;
-            *reinterpret_cast<double2 *>(C + m + (long long)j * p.C.ld) =
-                make_double2(acc[ni][mi][0], acc[ni][mi][1]);
-          }
-        }
-      }
-      const double wgt = diag_tile ? 1.0 : 2.0;
-      s_se *= wgt;
-      s_d2 *= wgt;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s_se += __shfl_xor_sync(0xffffffffu, s_se, o);
-        s_d2 += __shfl_xor_sync(0xffffffffu, s_d2, o);
-        s_tr += __shfl_xor_sync(0xffffffffu, s_tr, o);
-      }
-      if (lane == 0) {
-        red[warp * 3 + 0] = s_se;
-        red[warp * 3 + 1] = s_d2;
-        red[warp * 3 + 2] = s_tr;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        double r0 = 0, r1 = 0, r2 = 0;
-        for (int w8 = 0; w8 < NTHREADS / 32; w8++) {
-          r0 += red[w8 * 3 + 0];
-          r1 += red[w8 * 3 + 1];
-          r2 += red[w8 * 3 + 2];
-        }
-        const long long widx = (w - gridDim.x) % p.ntasks;
-        double *o = p.partial + (cur_b * p.ntasks + widx) * 4;
-        o[0] = r0;
-        o[1] = r1;
-        o[2] = r2;
-        o[3] = 0.0;
-      }
+        for (int mi = 0; mi < 8; mi++) dmma884(acc[ni][mi], bf[cur][ni], af[cur][mi]);
     }
-    if (!more) break;
   }
   cp_async_wait<0>();
+
+  if (EPI == EPI_AXPBY) {
+    double *__restrict__ C = p.C.p + b * p.C.stride;
+    const double *__restrict__ C0 = p.C0.p ? p.C0.p + b * p.C0.stride : nullptr;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const int n = task.c_c + wn + ni * 8 + g;
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        const int m = task.c_r + wm + mi * 8 + 2 * t;
+        double2 v = make_double2(alpha * acc[ni][mi][0], alpha * acc[ni][mi][1]);
+        if (C0) {
+          const double2 c0 = *reinterpret_cast<const double2 *>(C0 + m + (long long)n * p.C0.ld);
+          v.x = fma(beta, c0.x, v.x);
+          v.y = fma(beta, c0.y, v.y);
+        }
+        *reinterpret_cast<double2 *>(C + m + (long long)n * p.C.ld) = v;
+      }
+    }
+  } else {
+    // ---- fused trace epilogue: this tile of G = K^-1 never has to reach HBM -----------------
+    __syncthreads();  // everyone is done with the pipeline buffers
+    double *xr = smem, *xc = smem + TILE, *ar = smem + 2 * TILE, *ac = smem + 3 * TILE;
+    double *red = smem + 4 * TILE;
+    const double *x = p.x + b * p.x_stride;
+    const double *av = p.avec + b * p.a_stride;
+    if (tid < TILE) {
+      const int i = task.c_r + tid;
+      xr[tid] = (i < p.n) ? x[i] : 0.0;
+      ar[tid] = (i < p.n) ? av[i] : 0.0;
+    } else {
+      const int j = task.c_c + tid - TILE;
+      xc[tid - TILE] = (j < p.n) ? x[j] : 0.0;
+      ac[tid - TILE] = (j < p.n) ? av[j] : 0.0;
+    }
+    __syncthreads();
+    const double rho = p.theta[b * 3 + 1];
+    const double nh = -0.5 / (rho * rho);
+    const bool diag_tile = (task.flags & 1) != 0;
+    double s_se = 0.0, s_d2 = 0.0, s_tr = 0.0;
+    double *__restrict__ C = p.C.p ? p.C.p + b * p.C.stride : nullptr;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+      const int nl = wn + ni * 8 + g;
+      const int j = task.c_c + nl;
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int ml = wm + mi * 8 + 2 * t + e;
+          const int i = task.c_r + ml;
+          const double G = acc[ni][mi][e];
+          if (i < p.n && j < p.n) {
+            const double d = xr[ml] - xc[nl];
+            const double d2 = d * d;
+            const double ek = exp(d2 * nh);
+            const double M = ar[ml] * ac[nl] - G;
+            s_se += M * ek;
+            s_d2 += M * ek * d2;
+            if (diag_tile && i == j) s_tr += G;
+          }
+        }
+        if (C) {
+          const int m = task.c_r + wm + mi * 8 + 2 * t;
+          *reinterpret_cast<double2 *>(C + m + (long long)j * p.C.ld) =
+              make_double2(acc[ni][mi][0], acc[ni][mi][1]);
+        }
+      }
+    }
+    const double w = diag_tile ? 1.0 : 2.0;
+    s_se *= w;
+    s_d2 *= w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_se += __shfl_xor_sync(0xffffffffu, s_se, o);
+      s_d2 += __shfl_xor_sync(0xffffffffu, s_d2, o);
+      s_tr += __shfl_xor_sync(0xffffffffu, s_tr, o);
+    }
+    if (lane == 0) {
+      red[warp * 3 + 0] = s_se;
+      red[warp * 3 + 1] = s_d2;
+      red[warp * 3 + 2] = s_tr;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double r0 = 0, r1 = 0, r2 = 0;
+      for (int w8 = 0; w8 < NTHREADS / 32; w8++) {
+        r0 += red[w8 * 3 + 0];
+        r1 += red[w8 * 3 + 1];
+        r2 += red[w8 * 3 + 2];
+      }
+      double *o = p.partial + ((long long)b * p.ntasks + blockIdx.x) * 4;
+      o[0] = r0;
+      o[1] = r1;
+      o[2] = r2;
+      o[3] = 0.0;
+    }
+  }
 }
 
 template <bool A_KC, bool B_KC, int EPI>
-static int launch_one(Handle *h, const GemmParams &p_in, int ntasks, int batch) {
+static int launch_one(Handle *h, const GemmParams &p, int ntasks, int batch) {
   static bool configured = false;
-  static int num_sms = 0;
   auto kern = gemm_tile_kernel<A_KC, B_KC, EPI>;
   if (!configured) {
-    GPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL));
-    GPB_CUDA(h, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    GPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     configured = true;
   }
-  GemmParams p = p_in;
-  p.ntasks = ntasks;
-  const long long total = (long long)ntasks * batch;
-  const int grid = (int)std::min<long long>(total, num_sms);
+  dim3 grid(ntasks, batch);
   ProfScope ps__(h, PC_GEMM);
-  kern<<<grid, NTHREADS, GEMM_SMEM_TOTAL, h->stream>>>(p, total);
+  kern<<<grid, NTHREADS, GEMM_SMEM_BYTES, h->stream>>>(p);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

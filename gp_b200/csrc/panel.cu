@@ -103,6 +103,141 @@ potrf_tile_kernel(double *__restrict__ Lbase, long long ld, long long stride, lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// POTRF of one 128x128 tile, blocked (v2): right-looking over sixteen 8-column blocks with the tile
+// register-resident in mma accumulator layout (warp w owns rows 16w..16w+15, like the TRSM kernel):
+//   1. the warp that owns the 8x8 diagonal block factors it with warp shuffles (8 dependent steps)
+//   2. every warp solves its rows of the 8-column panel against that block (quad shuffles)
+//   3. rank-8 SYRK update of the trailing lower triangle with DMMA (mma.sync m8n8k4 f64); the panel
+//      goes through shared memory once per block (B operand), the A operand comes from registers
+// Two block barriers per 8 columns instead of one per column, and the O(n^3) part on the tensor pipe.
+// ------------------------------------------------------------------------------------------------
+constexpr int LD_P = 12;  // panel row stride in doubles: conflict-free B-operand reads ((12g + t) mod 16 distinct)
+
+__global__ void __launch_bounds__(256, 1)
+potrf_tile_kernel_v2(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
+                     int n, int *info) {
+  __shared__ __align__(16) double Dsm[2][64];         // Dsm[c*8 + r] = D[r][c] (factored diagonal block)
+  __shared__ double dinv[2][8];
+  __shared__ __align__(16) double Psm[2][TILE * LD_P];  // solved panel rows: Psm[row*LD_P + c]
+  __shared__ int s_info;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const unsigned FULL = 0xffffffffu;
+  const int qbase = lane & ~3;
+  double *T = Lbase + (long long)blockIdx.x * stride + diag_off;
+  const int r0 = warp * 16;
+  if (tid == 0) s_info = 0;
+
+  double acc[2][16][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 16; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int r = r0 + mt * 8 + g, c = nt * 8 + 2 * t + e;
+        acc[mt][nt][e] = (nt <= 2 * warp + mt) ? T[r + (long long)c * ld] : 0.0;  // tiles right of the diagonal are never used
+      }
+  __syncthreads();
+
+#pragma unroll
+  for (int cb = 0; cb < 16; cb++) {
+    const int buf = cb & 1;
+    // ---- 1. diagonal 8x8 block: rows 8cb..8cb+7 live in warp cb/2, m-tile cb%2 ------------------
+    if (warp == (cb >> 1)) {
+#pragma unroll
+      for (int mo = 0; mo < 2; mo++) {
+        if (mo == (cb & 1)) {
+          double a0 = acc[mo][cb][0], a1 = acc[mo][cb][1];  // element (row g, cols 2t, 2t+1)
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const double ak = (k & 1) ? a1 : a0;               // this lane's element in column k (valid if t == k/2)
+            const double piv = __shfl_sync(FULL, ak, 4 * k + (k >> 1));
+            if (!(piv > 0.0) && lane == 0 && s_info == 0) s_info = index_base + cb * 8 + k + 1;
+            const double inv = rsqrt(piv), dgl = piv * inv;  // shortest dependent chain on the critical path
+            const double lrow = __shfl_sync(FULL, ak, 4 * g + (k >> 1)) * inv;            // l[g][k]
+            const double lc0 = __shfl_sync(FULL, ak, 4 * (2 * t) + (k >> 1)) * inv;       // l[2t][k]
+            const double lc1 = __shfl_sync(FULL, ak, 4 * (2 * t + 1) + (k >> 1)) * inv;   // l[2t+1][k]
+            if (2 * t > k && g >= 2 * t) a0 = fma(-lrow, lc0, a0);
+            if (2 * t + 1 > k && g >= 2 * t + 1) a1 = fma(-lrow, lc1, a1);
+            if (t == (k >> 1)) {  // write the finished column k
+              const double v = (g > k) ? lrow : ((g == k) ? dgl : 0.0);
+              if (k & 1) a1 = v; else a0 = v;
+            }
+          }
+          // strict upper part of the block -> exact zeros
+          if (2 * t > g) a0 = 0.0;
+          if (2 * t + 1 > g) a1 = 0.0;
+          acc[mo][cb][0] = a0;
+          acc[mo][cb][1] = a1;
+          Dsm[buf][(2 * t) * 8 + g] = a0;
+          Dsm[buf][(2 * t + 1) * 8 + g] = a1;
+          if (g == 2 * t) dinv[buf][g] = 1.0 / a0;
+          if (g == 2 * t + 1) dinv[buf][g] = 1.0 / a1;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 2. panel solve for the m-tiles strictly below the diagonal block ------------------------
+    double af[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+      const bool below = (2 * warp + mt) > cb;  // warp-uniform
+      if (below) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          double xv = acc[mt][cb][c & 1] * dinv[buf][c];
+          if (t == (c >> 1)) acc[mt][cb][c & 1] = xv;
+          xv = __shfl_sync(FULL, xv, qbase + (c >> 1));
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int cp = 2 * t + e;
+            if (cp > c) acc[mt][cb][e] = fma(-xv, Dsm[buf][c * 8 + cp], acc[mt][cb][e]);
+          }
+        }
+        *reinterpret_cast<double2 *>(&Psm[buf][(r0 + mt * 8 + g) * LD_P + 2 * t]) =
+            make_double2(acc[mt][cb][0], acc[mt][cb][1]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        const int src = qbase + 2 * ks + (t >> 1);
+        const double v0 = __shfl_sync(FULL, acc[mt][cb][0], src);
+        const double v1 = __shfl_sync(FULL, acc[mt][cb][1], src);
+        af[mt][ks] = (t & 1) ? v1 : v0;
+      }
+    }
+    __syncthreads();
+    // ---- 3. trailing update, lower triangle only: C[i][j] -= X[i] . X[j], 8cb+7 < j <= i ---------
+#pragma unroll
+    for (int nt = 0; nt < 16; nt++) {
+      if (nt > cb && nt <= 2 * warp + 1) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          const double bfv = -Psm[buf][(nt * 8 + g) * LD_P + ks * 4 + t];
+          if (nt <= 2 * warp) dmma884p(acc[0][nt], af[0][ks], bfv);
+          dmma884p(acc[1][nt], af[1][ks], bfv);
+        }
+      }
+    }
+  }
+
+  // write back: lower triangle = L, strict upper = 0 (Eigen matrixL() convention)
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 16; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int r = r0 + mt * 8 + g, c = nt * 8 + 2 * t + e;
+        T[r + (long long)c * ld] = (r >= c) ? acc[mt][nt][e] : 0.0;
+      }
+  __syncthreads();
+  if (tid == 0 && s_info != 0 && s_info <= n) {
+    if (info[blockIdx.x] == 0) info[blockIdx.x] = s_info;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // TRSM tile: X L^T = C with L the 128x128 lower-triangular diagonal tile, C a 128x128 tile.
 // 8 warps; warp w owns rows 16w..16w+15 as two m8 mma row tiles x sixteen n8 column tiles.
 // MODE 0: C read from / X written to the tile (in place).  MODE 1: C = I, X^T written to Wout
@@ -124,16 +259,8 @@ trsm_tile_kernel(const double *Ldiag_base, double *Cbase, long long ld, long lon
   const double *Ld = Ldiag_base + (long long)item * stride + diag_off + (long long)blockIdx.x * diag_step;
   double *Ct = Cbase + (long long)item * stride + c_off + (long long)blockIdx.x * c_step;
 
-  // stage the diagonal tile (column-major copy, 16B vectors)
-  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
-    const int k = idx >> 6, n2 = idx & 63;
-    const double2 v = *reinterpret_cast<const double2 *>(Ld + 2 * n2 + (long long)k * ld);
-    *reinterpret_cast<double2 *>(Ls + k * LD_L + 2 * n2) = v;
-  }
-  __syncthreads();
-  if (tid < TILE) invd[tid] = 1.0 / Ls[tid * LD_L + tid];
-  __syncthreads();
-
+  // the C tile goes straight to registers; issue those loads first so that they overlap the staging
+  // of the diagonal tile (both are 128 KB and this kernel runs one CTA per SM)
   double acc[2][16][2];
   const int r0 = warp * 16;
 #pragma unroll
@@ -145,6 +272,16 @@ trsm_tile_kernel(const double *Ldiag_base, double *Cbase, long long ld, long lon
         const int r = r0 + mt * 8 + g, c = nt * 8 + 2 * t + e;
         acc[mt][nt][e] = (MODE == 0) ? Ct[r + (long long)c * ld] : ((r == c) ? 1.0 : 0.0);
       }
+
+  // stage the diagonal tile (column-major copy, 16B vectors)
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+    const int k = idx >> 6, n2 = idx & 63;
+    const double2 v = *reinterpret_cast<const double2 *>(Ld + 2 * n2 + (long long)k * ld);
+    *reinterpret_cast<double2 *>(Ls + k * LD_L + 2 * n2) = v;
+  }
+  __syncthreads();
+  if (tid < TILE) invd[tid] = 1.0 / Ls[tid * LD_L + tid];
+  __syncthreads();
 
   const unsigned FULL = 0xffffffffu;
   const int qbase = lane & ~3;
@@ -220,7 +357,7 @@ int panel_smem_setup(Handle *h) {
 int launch_potrf_tile_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, int index_base,
                          int n, int batch, int *info) {
   ProfScope ps__(h, PC_POTRF);
-  potrf_tile_kernel<<<batch, 256, 0, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
+  potrf_tile_kernel_v2<<<batch, 256, 0, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
