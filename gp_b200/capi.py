@@ -44,6 +44,8 @@ SIGNATURES = {
     "gpb200_gram_se": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int]),
     "gpb200_gram_deriv": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_double,
                                     C.c_int, C.c_void_p, C.c_int]),
+    "gpb200_approx_L_basis": (C.c_int, [_h, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                        C.c_int]),
     "gpb200_potrf": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_int]),
     "gpb200_trsm_lower": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "gpb200_potrs": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -54,6 +56,8 @@ SIGNATURES = {
     "gpb200_lml_grad_batched": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, _ll, C.c_void_p,
                                           C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpb200_rbf_cov_chol": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "gpb200_rbf_cov_chol_batched": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
     "gpb200_se_chol_tangent": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
                                          C.c_void_p, C.c_void_p]),
     "gpb200_approx_L": (C.c_int, [_h, C.c_int, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
@@ -230,6 +234,14 @@ class Handle:
                                                int(quirk), _ptr(K), max(N, 1)), "gram_deriv")
         return K
 
+    def approx_L_basis(self, M, scale, x, sigma, l):
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        n = x.shape[0]
+        out = np.empty((n, M), order="F")
+        self._check(self.lib.gpb200_approx_L_basis(self._h, n, int(M), scale, _ptr(x), sigma, l, _ptr(out), max(n, 1)),
+                    "approx_L_basis")
+        return out
+
     # -- a6-a8 ----------------------------------------------------------------------------------
     def potrf(self, A, raise_on_info=True):
         A = np.array(A, dtype=np.float64, order="F", copy=True)
@@ -315,6 +327,19 @@ class Handle:
         L = np.empty((n, n), order="F"); dL = np.empty((n, n), order="F")
         self._check(self.lib.gpb200_rbf_cov_chol(self._h, n, _ptr(x1), l, _ptr(L), _ptr(dL)), "rbf_cov_chol")
         return L, dL
+
+    def rbf_cov_chol_batched(self, x1, ls):
+        """Tables for approx_L: returns (Ls, dLdls) as arrays of shape (P, n, n) [each slice column-major]."""
+        x1 = np.ascontiguousarray(x1, dtype=np.float64).ravel()
+        ls = np.ascontiguousarray(ls, dtype=np.float64).ravel()
+        n, P = x1.shape[0], ls.shape[0]
+        L = np.empty((P, n, n)); dL = np.empty((P, n, n)); info = np.zeros(P, dtype=np.int32)
+        self._check(self.lib.gpb200_rbf_cov_chol_batched(self._h, n, _ptr(x1), P, _ptr(ls), _ptr(L), _ptr(dL),
+                                                         _ptr(info)), "rbf_cov_chol_batched")
+        if np.any(info > 0):
+            raise NotPositiveDefiniteError("rbf_cov_chol_batched", int(info[info > 0][0]))
+        # each slice was written column-major: expose as Fortran-ordered matrices
+        return [L[q].T.copy(order="F") for q in range(P)], [dL[q].T.copy(order="F") for q in range(P)]
 
     def se_chol_tangent(self, x, alpha, rho, diag_add, wrt):
         """L = chol(cov_exp_quad(x, alpha, rho) + diag_add I) and dL/d(alpha if wrt == 0 else rho)."""

@@ -21,3 +21,9 @@ def approx_L(l, lp, Ls, dLdls, handle=None):
 
 def approx_Lz(l, lp, Ls, dLdls, z, handle=None):
     return (handle or capi.default_handle()).approx_Lz(float(l), lp, Ls, dLdls, z)
+
+
+def rbf_cov_chol_grid(x1, lp, handle=None):
+    """All P tables of a length-scale grid in one batched GPU call (what models/interpolated_gp.stan:15-21
+    and the data block of models/cubic_interpolated_gp.stan:11-12 need): returns (Ls, dLdls)."""
+    return (handle or capi.default_handle()).rbf_cov_chol_batched(x1, lp)

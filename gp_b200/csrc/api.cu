@@ -529,6 +529,22 @@ extern "C" int gpb200_gram_deriv(gpb200_handle_t h, int n, const double *t, doub
   return finish(h);
 }
 
+extern "C" int gpb200_approx_L_basis(gpb200_handle_t h, int n, int M, double scale, const double *x, double sigma,
+                                     double l, double *out, int ldo) {
+  CHECK_H(h);
+  if (n < 0 || M < 1) BAD_ARG(h, 2, "approx_L_basis: bad sizes");
+  if (ldo < std::max(1, n)) BAD_ARG(h, 9, "approx_L_basis: ldo < n");
+  if (n == 0) return 0;
+  if (h->device_ptrs) return launch_approx_basis(h, n, M, scale, x, sigma, l, out, ldo);
+  Arena a;
+  RC(ws_reserve(h, pad256(n * 8) + pad256((size_t)n * M * 8), &a));
+  double *dx = a.take<double>(n), *dout = a.take<double>((size_t)n * M);
+  RC(to_device(h, x, dx, n));
+  RC(launch_approx_basis(h, n, M, scale, dx, sigma, l, dout, n));
+  RC(from_device_2d(h, dout, n, out, ldo, n, M));
+  return finish(h);
+}
+
 // =================================================================================================
 // a6-a8 factorisation and solves on caller matrices
 // =================================================================================================
@@ -870,54 +886,62 @@ int tasks_tangent(Handle *h, int nt, TaskList *t1, TaskList *ta, TaskList *tl) {
 
 namespace {
 // L = chol(S), dL = L Phi(L^-1 Sdot L^-T) for the Gram/tangent pair selected by `mode`
-int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, double l, double dadd, int mode, double *L,
-                        double *dLdl) {
+int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, const double *ls_host, int P, double dadd,
+                        int mode, double *L, double *dLdl, int *info_out_host) {
   const int np = round_up(n, TILE), nt = np / TILE;
   const size_t mat = (size_t)np * np;
+  const long long st = (long long)mat;
   Arena a;
-  RC(ws_reserve(h, 4 * pad256(mat * 8) + pad256(n * 8) + pad256((size_t)n * n * 8) + 1024, &a));
-  double *Lbuf = a.take<double>(mat), *Sbuf = a.take<double>(mat), *Dbuf = a.take<double>(mat), *Lkeep = a.take<double>(mat);
-  double *dx = a.take<double>(n);
-  int *info = a.take<int>(1);
+  RC(ws_reserve(h, 4 * P * pad256(mat * 8) + pad256(n * 8) + pad256((size_t)n * n * 8) + pad256(P * 8) + pad256(P * 4) + 2048, &a));
+  double *Lbuf = a.take<double>(mat * P), *Sbuf = a.take<double>(mat * P), *Dbuf = a.take<double>(mat * P),
+         *Lkeep = a.take<double>(mat * P);
+  double *dx = a.take<double>(n), *dls = a.take<double>(P);
+  int *info = a.take<int>(P);
   double *stage = h->device_ptrs ? nullptr : a.take<double>((size_t)n * n);
-  GPB_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int), h->stream));
+  if (!info || (!h->device_ptrs && !stage)) BAD_ARG(h, 1002, "chol_tangent: workspace exhausted");
+  GPB_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * P, h->stream));
   RC(to_device(h, x1, dx, n));
-  RC(launch_gram_tangent(h, n, np, dx, alpha, l, dadd, mode, Lbuf, Dbuf));
-  RC(chol_batched(h, Lbuf, np, (long long)mat, n, 1, info, nullptr));
-  int hinfo = 0;
-  RC(read_info(h, info, &hinfo));
-  GPB_CUDA(h, cudaMemcpyAsync(Lkeep, Lbuf, mat * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  RC(trtri_batched(h, Lbuf, Sbuf, np, (long long)mat, 1));
+  GPB_CUDA(h, cudaMemcpyAsync(dls, ls_host, sizeof(double) * P, cudaMemcpyHostToDevice, h->stream));
+  GPB_CUDA(h, cudaStreamSynchronize(h->stream));  // ls_host may be a stack temporary
+  RC(launch_gram_tangent(h, n, np, dx, alpha, dls, dadd, mode, Lbuf, Dbuf, st, P));
+  RC(chol_batched(h, Lbuf, np, st, n, P, info, nullptr));
+  GPB_CUDA(h, cudaMemcpyAsync(info_out_host, info, sizeof(int) * P, cudaMemcpyDeviceToHost, h->stream));
+  GPB_CUDA(h, cudaMemcpyAsync(Lkeep, Lbuf, mat * P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  RC(trtri_batched(h, Lbuf, Sbuf, np, st, P));
   TaskList t1, ta, tl;
   RC(tasks_tangent(h, nt, &t1, &ta, &tl));
   {  // T1 = W Kdot  -> Sbuf (lower tiles)
     GemmParams p{};
-    p.A = mref(Lbuf, np, 0); p.B = mref(Dbuf, np, 0); p.C = mref(Sbuf, np, 0); p.alpha = 1.0; p.tasks = t1.at(0);
-    RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, t1.count(0), 1));
+    p.A = mref(Lbuf, np, st); p.B = mref(Dbuf, np, st); p.C = mref(Sbuf, np, st); p.alpha = 1.0; p.tasks = t1.at(0);
+    RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, t1.count(0), P));
   }
   {  // A = T1 W^T -> Dbuf (lower tiles)
     GemmParams p{};
-    p.A = mref(Sbuf, np, 0); p.B = mref(Lbuf, np, 0); p.C = mref(Dbuf, np, 0); p.alpha = 1.0; p.tasks = ta.at(0);
-    RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, ta.count(0), 1));
+    p.A = mref(Sbuf, np, st); p.B = mref(Lbuf, np, st); p.C = mref(Dbuf, np, st); p.alpha = 1.0; p.tasks = ta.at(0);
+    RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, ta.count(0), P));
   }
-  RC(launch_phi_lower(h, np, Dbuf));
+  RC(launch_phi_lower(h, np, Dbuf, st, P));
   {  // Ldot = L Phi(A) -> Sbuf (lower tiles)
     GemmParams p{};
-    p.A = mref(Lkeep, np, 0); p.B = mref(Dbuf, np, 0); p.C = mref(Sbuf, np, 0); p.alpha = 1.0; p.tasks = tl.at(0);
-    RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, tl.count(0), 1));
+    p.A = mref(Lkeep, np, st); p.B = mref(Dbuf, np, st); p.C = mref(Sbuf, np, st); p.alpha = 1.0; p.tasks = tl.at(0);
+    RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, tl.count(0), P));
   }
-  if (h->device_ptrs) {
-    RC(launch_unpack(h, n, n, Lkeep, np, L, n, 1, 0.0));
-    RC(launch_unpack(h, n, n, Sbuf, np, dLdl, n, 1, 0.0));
-  } else {
-    RC(launch_unpack(h, n, n, Lkeep, np, stage, n, 1, 0.0));
-    RC(from_device(h, stage, L, (size_t)n * n * sizeof(double)));
-    GPB_CUDA(h, cudaStreamSynchronize(h->stream));
-    RC(launch_unpack(h, n, n, Sbuf, np, stage, n, 1, 0.0));
-    RC(from_device(h, stage, dLdl, (size_t)n * n * sizeof(double)));
+  const size_t nn = (size_t)n * n;
+  for (int q = 0; q < P; q++) {
+    if (h->device_ptrs) {
+      RC(launch_unpack(h, n, n, Lkeep + q * mat, np, L + q * nn, n, 1, 0.0));
+      RC(launch_unpack(h, n, n, Sbuf + q * mat, np, dLdl + q * nn, n, 1, 0.0));
+    } else {
+      RC(launch_unpack(h, n, n, Lkeep + q * mat, np, stage, n, 1, 0.0));
+      RC(from_device(h, stage, L + q * nn, nn * sizeof(double)));
+      GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+      RC(launch_unpack(h, n, n, Sbuf + q * mat, np, stage, n, 1, 0.0));
+      RC(from_device(h, stage, dLdl + q * nn, nn * sizeof(double)));
+      GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
   }
-  RC(finish(h));
-  return hinfo;
+  GPB_CUDA(h, cudaStreamSynchronize(h->stream));  // info_out_host is valid from here
+  return 0;
 }
 }  // namespace
 
@@ -925,7 +949,21 @@ extern "C" int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, d
   CHECK_H(h);
   if (n < 0) BAD_ARG(h, 2, "rbf_cov_chol: negative n");
   if (n == 0) return 0;
-  return chol_tangent_common(h, n, x1, 1.0, l, 1e-10, 0, L, dLdl);
+  int info = 0;
+  RC(chol_tangent_common(h, n, x1, 1.0, &l, 1, 1e-10, 0, L, dLdl, &info));
+  return info;
+}
+
+// P length-scales in one call: the tables Ls[P], dLdls[P] that approx_L / approx_Lz interpolate
+// (models/interpolated_gp.stan:15-21 builds them with P separate Choleskys; test_interpolate.R:9 uses
+// P = 10).  ls and info are HOST arrays of length P; L, dLdl hold P consecutive n x n matrices.
+extern "C" int gpb200_rbf_cov_chol_batched(gpb200_handle_t h, int n, const double *x1, int P, const double *ls,
+                                           double *L, double *dLdl, int *info) {
+  CHECK_H(h);
+  if (n < 0) BAD_ARG(h, 2, "rbf_cov_chol_batched: negative n");
+  if (P < 0) BAD_ARG(h, 4, "rbf_cov_chol_batched: negative P");
+  if (n == 0 || P == 0) return 0;
+  return chol_tangent_common(h, n, x1, 1.0, ls, P, 1e-10, 0, L, dLdl, info);
 }
 
 extern "C" int gpb200_se_chol_tangent(gpb200_handle_t h, int n, const double *x, double alpha, double rho,
@@ -934,7 +972,9 @@ extern "C" int gpb200_se_chol_tangent(gpb200_handle_t h, int n, const double *x,
   if (n < 0) BAD_ARG(h, 2, "se_chol_tangent: negative n");
   if (wrt != 0 && wrt != 1) BAD_ARG(h, 7, "se_chol_tangent: wrt must be 0 (alpha) or 1 (rho)");
   if (n == 0) return 0;
-  return chol_tangent_common(h, n, x, alpha, rho, diag_add, wrt == 1 ? 1 : 2, L, dL);
+  int info = 0;
+  RC(chol_tangent_common(h, n, x, alpha, &rho, 1, diag_add, wrt == 1 ? 1 : 2, L, dL, &info));
+  return info;
 }
 
 namespace {

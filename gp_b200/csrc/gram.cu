@@ -147,8 +147,12 @@ __global__ void __launch_bounds__(256) gram_se_panel_kernel(int n, int np, const
 // mode 1: cov_exp_quad form, tangent w.r.t. rho:   S = alpha^2 exp(-0.5 d^2/rho^2) + c I, dS/drho = S_se d^2/rho^3
 // mode 2: cov_exp_quad form, tangent w.r.t. alpha: dS/dalpha = 2 alpha exp(-0.5 d^2/rho^2)
 __global__ void __launch_bounds__(256) gram_tangent_kernel(int n, int np, const double *__restrict__ x, double alpha,
-                                                          double l, double dadd, int mode, double *__restrict__ S,
-                                                          double *__restrict__ Sdot) {
+                                                          const double *__restrict__ ls, double dadd, int mode,
+                                                          double *__restrict__ S, double *__restrict__ Sdot,
+                                                          long long stride) {
+  const double l = ls[blockIdx.z];
+  S += (long long)blockIdx.z * stride;
+  Sdot += (long long)blockIdx.z * stride;
   __shared__ double xs[TILE], ys[TILE];
   const int r0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE, tid = threadIdx.x;
   if (tid < TILE) xs[tid] = (r0 + tid < n) ? x[r0 + tid] : 0.0;
@@ -229,6 +233,48 @@ __global__ void __launch_bounds__(256) gram_ard_kernel(int n, int m, int D, cons
   }
 }
 
+// ---- f-3: Mercer / Hermite eigen-basis factor of the SE kernel ---------------------------------
+// approx_L(M, scale, x, sigma, l) of models/westbrook.stan:2-30 (copied into six other models;
+// spectral_test.R:6-27 `bH`): N x M matrix whose columns are scaled Hermite functions built by a
+// three-term recurrence, with L L^T ~ cov_exp_quad(x, sigma, l).  One thread per row, columns written
+// coalesced; HBM-bound (8 N M bytes).
+__global__ void approx_basis_kernel(int n, int M, double scale, const double *__restrict__ x, double sigma, double l,
+                                    double *__restrict__ out, long long ldo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = 1.0 / (4.0 * scale * scale);
+  const double b = 1.0 / (2.0 * l * l);
+  const double epsilon = sqrt(b);
+  const double alpha = sqrt(2.0 * a);
+  const double r = 2.0 * epsilon / alpha;
+  const double beta = sqrt(sqrt(1.0 + r * r));
+  const double delta = sqrt(alpha * alpha * (beta * beta - 1.0) / 2.0);
+  const double denom = alpha * alpha + delta * delta + epsilon * epsilon;
+  const double xi = x[i];
+  const double xp = alpha * beta * xi;
+  const double f = sqrt(epsilon * epsilon / denom);
+  double h1 = sqrt(sqrt(alpha * alpha / denom)) * sqrt(beta) * exp(-delta * delta * xi * xi);
+  out[i] = sigma * h1;
+  if (M < 2) return;
+  double h2 = f * sqrt(1.0 / 2.0) * 2.0 * xp * h1;
+  out[i + ldo] = sigma * h2;
+  for (int k = 3; k <= M; k++) {
+    const double h3 = f * sqrt(1.0 / (2.0 * (k - 1))) * 2.0 * xp * h2 -
+                      f * f * sqrt(1.0 / (4.0 * (k - 1) * (double)(k - 2))) * 2.0 * (k - 2) * h1;
+    out[i + (long long)(k - 1) * ldo] = sigma * h3;
+    h1 = h2;
+    h2 = h3;
+  }
+}
+
+int launch_approx_basis(Handle *h, int n, int M, double scale, const double *x, double sigma, double l, double *out,
+                        long long ldo) {
+  ProfScope ps__(h, PC_GRAM);
+  approx_basis_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(n, M, scale, x, sigma, l, out, ldo);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 int launch_kernel_eval(Handle *h, int kind, long long len, const double *tj, const double *tk, double amp2,
                        double l, double *out) {
@@ -269,11 +315,11 @@ int launch_gram_se_panel(Handle *h, int n, int np, const double *x, double alpha
   return 0;
 }
 
-int launch_gram_tangent(Handle *h, int n, int np, const double *x, double alpha, double l, double dadd, int mode,
-                        double *S, double *Sdot) {
-  dim3 grid(np / TILE, np / TILE);
+int launch_gram_tangent(Handle *h, int n, int np, const double *x, double alpha, const double *ls, double dadd, int mode,
+                        double *S, double *Sdot, long long stride, int batch) {
+  dim3 grid(np / TILE, np / TILE, batch);
   ProfScope ps__(h, PC_GRAM);
-  gram_tangent_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, alpha, l, dadd, mode, S, Sdot);
+  gram_tangent_kernel<<<grid, 256, 0, h->stream>>>(n, np, x, alpha, ls, dadd, mode, S, Sdot, stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

@@ -12,12 +12,15 @@ int launch_gram_outer(Handle *h, int kind, int n, int m, const double *x, const 
                       double *K, long long ldk);
 int launch_gram_se_batched(Handle *h, int n, int np, const double *x, long long x_stride, const double *theta,
                            double jitter, int lower_only, double *K, long long stride, int batch);
-int launch_gram_tangent(Handle *h, int n, int np, const double *x, double alpha, double l, double dadd, int mode,
-                        double *S, double *Sdot);
+int launch_gram_tangent(Handle *h, int n, int np, const double *x, double alpha, const double *ls, double dadd, int mode,
+                        double *S, double *Sdot, long long stride, int batch);
 int launch_gram_deriv(Handle *h, int n, int nblocks, const double *t, double alpha, double rho, const double *noise,
                       double jitter, int quirk, double *K, long long ldk);
 int launch_gram_ard(Handle *h, int n, int m, int D, const double *X, long long ldx, const double *Y, long long ldy,
                     double alpha, const double *rho, int rho_len, double *K, long long ldk);
+
+int launch_approx_basis(Handle *h, int n, int M, double scale, const double *x, double sigma, double l, double *out,
+                        long long ldo);
 
 // solve.cu
 int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, const double *y, long long y_stride,
@@ -42,7 +45,7 @@ int launch_pack(Handle *h, int rows, int cols, const double *src, long long lds,
                 int mode, double diag_add);
 int launch_unpack(Handle *h, int rows, int cols, const double *src, long long lds_src, double *dst, long long ldd,
                   int mode, double diag_add);
-int launch_phi_lower(Handle *h, int np, double *A);
+int launch_phi_lower(Handle *h, int np, double *A, long long stride, int batch);
 int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv, const double *z, const double *add,
                   double *out);
 int launch_hermite(Handle *h, long long len, int n, const double *y1, const double *y2, const double *k1,

@@ -285,7 +285,8 @@ __global__ void unpack_kernel(int rows, int cols, const double *__restrict__ src
 
 // Phi for the forward-mode Cholesky tangent: keep the lower triangle, halve the diagonal, zero the
 // strict upper part (only the diagonal tiles contain upper entries that are ever read).
-__global__ void phi_lower_kernel(int np, double *__restrict__ A) {
+__global__ void phi_lower_kernel(int np, double *__restrict__ A, long long stride) {
+  A += (long long)blockIdx.z * stride;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
   if (i >= np) return;
@@ -425,10 +426,10 @@ int launch_unpack(Handle *h, int rows, int cols, const double *src, long long ld
   return 0;
 }
 
-int launch_phi_lower(Handle *h, int np, double *A) {
-  dim3 grid((np + 255) / 256, np);
+int launch_phi_lower(Handle *h, int np, double *A, long long stride, int batch) {
+  dim3 grid((np + 255) / 256, np, batch);
   ProfScope ps__(h, PC_OTHER);
-  phi_lower_kernel<<<grid, 256, 0, h->stream>>>(np, A);
+  phi_lower_kernel<<<grid, 256, 0, h->stream>>>(np, A, stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

@@ -94,6 +94,11 @@ GPB200_API int gpb200_gram_deriv(gpb200_handle_t h, int n, const double *t, doub
                       int nblocks, const double *noise, double jitter, int quirk, double *K,
                       int ldk);
 
+/* f-3: approx_L(M, scale, xt, sigma, l) of models/westbrook.stan:2-30 (and its six copies;
+ * spectral_test.R:6-27 bH): N x M eigen-basis factor, out out^T ~ cov_exp_quad(x, sigma, l). */
+GPB200_API int gpb200_approx_L_basis(gpb200_handle_t h, int n, int M, double scale, const double *x,
+                                     double sigma, double l, double *out, int ldo);
+
 /* ---- a6-a8: factorisation, solves, likelihood ------------------------------------------------ */
 /* cholesky_decompose (fit_hyperparameters.stan:25; covariance.cpp:29; R chol spectral_test.R:32):
  * in place, lower; the strict upper triangle is zeroed like Eigen's matrixL(). */
@@ -136,6 +141,12 @@ GPB200_API int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
  * upper triangle. */
 GPB200_API int gpb200_rbf_cov_chol(gpb200_handle_t h, int n, const double *x1, double l, double *L,
                         double *dLdl);
+
+/* The same for P length-scales in one call: the tables Ls[P], dLdls[P] that approx_L / approx_Lz
+ * interpolate (models/interpolated_gp.stan:15-21 builds them with P separate Choleskys;
+ * test_interpolate.R:9 uses P = 10).  ls, info: HOST arrays of length P; L, dLdl: P consecutive n x n. */
+GPB200_API int gpb200_rbf_cov_chol_batched(gpb200_handle_t h, int n, const double *x1, int P, const double *ls,
+                                           double *L, double *dLdl, int *info);
 
 /* Generalisation used by the non-centred latent models (exact_gp.stan:17-25 alpha = 1, diag_add =
  * 1e-10; fit_full_gp.stan:18-26; heteroscedastic.stan:23-32): L = chol(cov_exp_quad(x, alpha, rho) +

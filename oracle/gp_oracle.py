@@ -554,3 +554,24 @@ def create_p_dotXnS(Xn_list, mn, Kn, theta, normals, sd_is_variance=True):
         st["Xs"] = np.vstack([st["Xs"], xs]); st["d"] = np.append(st["d"], dot_xs)
         return {"mu": float(cmean), "sigma": float(cvar), "dot_xs": float(dot_xs)}
     return call
+
+
+# f-3: eigen-basis factor (models/westbrook.stan:2-30; spectral_test.R:6-27)
+def approx_L_basis(M, scale, xt, sigma, l):
+    x = np.asarray(xt, dtype=np.float64)
+    a = 1.0 / (4.0 * scale ** 2)
+    b = 1.0 / (2.0 * l ** 2)
+    epsilon = math.sqrt(b)
+    alpha = math.sqrt(2.0 * a)
+    beta = (1.0 + (2.0 * epsilon / alpha) ** 2) ** 0.25
+    delta = math.sqrt(alpha ** 2 * (beta ** 2 - 1.0) / 2.0)
+    Ht = np.zeros((x.shape[0], M))
+    xp = alpha * beta * x
+    f = math.sqrt(epsilon ** 2 / (alpha ** 2 + delta ** 2 + epsilon ** 2))
+    Ht[:, 0] = math.sqrt(math.sqrt(alpha ** 2 / (alpha ** 2 + delta ** 2 + epsilon ** 2))) * math.sqrt(beta) * np.exp(-delta ** 2 * x * x)
+    if M > 1:
+        Ht[:, 1] = f * math.sqrt(1.0 / 2) * 2.0 * xp * Ht[:, 0]
+    for n in range(3, M + 1):
+        Ht[:, n - 1] = (f * math.sqrt(1.0 / (2.0 * (n - 1))) * 2.0 * xp * Ht[:, n - 2]
+                        - f ** 2 * math.sqrt(1.0 / (4.0 * (n - 1) * (n - 2))) * 2.0 * (n - 2) * Ht[:, n - 3])
+    return sigma * Ht

@@ -156,3 +156,35 @@ def test_create_p_dotXnS_sequential_sampler(handle):
     with pytest.raises(NotPositiveDefiniteError):
         for xs in (0.9, 1.7, 2.5):
             fq([xs])
+
+
+def test_rbf_cov_chol_grid_and_interpolation(handle):
+    # test_interpolate.R:9 grid: lp = seq(qgamma(.05,4,4), qgamma(.95,4,4), length = 10) ~ [0.34, 1.94]
+    from gp_b200 import covariance as cv
+    x1 = np.arange(60) * 1.5
+    lp = np.linspace(0.3416, 1.938, 10)
+    Ls, dLs = cv.rbf_cov_chol_grid(x1, lp, handle=handle)
+    for q in (0, 4, 9):
+        Lr, dLr = o.rbf_cov_chol(x1, float(lp[q]))
+        assert relerr(Ls[q], Lr) < 1e-9 and relerr(dLs[q], dLr) < 1e-8
+        single = cv.rbf_cov_chol(x1, float(lp[q]), handle=handle)
+        assert np.array_equal(single["L"], Ls[q]) and np.array_equal(single["dLdl"], dLs[q])
+    # cubic Hermite interpolation between the tabulated factors approximates the exact factor
+    l = 0.9
+    approx = cv.approx_L(l, lp, Ls, dLs, handle=handle)
+    exact, _ = o.rbf_cov_chol(x1, l)
+    assert relerr(approx, exact) < 1e-3
+
+
+def test_eigen_basis_approx_L(handle):
+    # models/westbrook.stan:2-30 + its self-check (:72); westbrook.R:22 uses M = 10, scale ~ 0.25 on x in [-0.5, 0.5]
+    from gp_b200 import approx_gp
+    x = np.linspace(-0.5, 0.5, 300)
+    for M in (1, 2, 10, 20):
+        L = approx_gp.approx_L(M, 0.25, x, 1.3, 0.4, handle=handle)
+        assert L.shape == (300, M) and relerr(L, o.approx_L_basis(M, 0.25, x, 1.3, 0.4)) < 1e-12
+    e10 = approx_gp.approx_error(10, 0.25, x, 1.0, 0.4, handle=handle)
+    e20 = approx_gp.approx_error(20, 0.25, x, 1.0, 0.4, handle=handle)
+    Lr = o.approx_L_basis(20, 0.25, x, 1.0, 0.4)
+    ref20 = np.log10(np.max(np.abs(o.cov_exp_quad(x, 1.0, 0.4) - Lr @ Lr.T)) + 1e-20)
+    assert e20 < e10 < 0 and abs(e20 - ref20) < 1e-6
