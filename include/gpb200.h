@@ -44,7 +44,8 @@ GPB200_API int gpb200_synchronize(gpb200_handle_t h);
 GPB200_API const char *gpb200_last_error(gpb200_handle_t h);
 GPB200_API long long gpb200_launch_count(gpb200_handle_t h);            /* kernels launched by this handle   */
 GPB200_API int gpb200_version(void);
-/* cap on the device workspace the batched entry points may allocate (bytes; 0 = 60% of free) */
+/* cap on the device workspace the batched entry points may use (bytes; 0 = 85% of free memory);
+ * a batch that does not fit is processed in chunks with identical results */
 GPB200_API int gpb200_set_workspace_limit(gpb200_handle_t h, long long bytes);
 
 /* tuning/testing knob: Cholesky panel width in 128-column tiles (0 = automatic: pure left-looking

@@ -9,6 +9,12 @@ dyn.load(file.path(Sys.getenv("GPB200_HOME", "."), "r", "gpb200_r.so"))
 # ---- covariance.cpp -----------------------------------------------------------------------------
 rbf_cov_chol <- function(x1, l_) .Call("gp_rbf_cov_chol", as.double(x1), as.double(l_))
 approx_L <- function(l, lp, Ls, dLdls) .Call("gp_approx_L", as.double(l), as.double(lp), Ls, dLdls)
+# all tables of a length-scale grid in one GPU call: tabs <- rbf_cov_chol_grid(x, lp); tabs$Ls, tabs$dLdls
+rbf_cov_chol_grid <- function(x1, lp) .Call("gp_rbf_cov_chol_grid", as.double(x1), as.double(lp))
+# eigen-basis factor of models/westbrook.stan:2-30 (named approx_L there too; bH in spectral_test.R:6)
+bH <- function(M, scale, x, sigma, l) .Call("gp_approx_L_basis", as.integer(M), as.double(scale), as.double(x), as.double(sigma), as.double(l))
+# latent models: Cholesky and its tangent (wrt = 0 alpha, 1 rho)
+se_chol_tangent <- function(x, alpha, rho, diag_add, wrt) .Call("gp_se_chol_tangent", as.double(x), as.double(alpha), as.double(rho), as.double(diag_add), as.integer(wrt))
 
 # ---- derivative_kernels.R:39-73 (element-wise closures, vectorised like the originals) ------------
 .gp_elem <- function(kind) function(tj, tk, l) {

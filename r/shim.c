@@ -12,6 +12,9 @@
  * R is single-threaded: all entry points run on the main R thread and synchronise before returning
  * (host-pointer mode of the ABI).  Outputs are R-allocated and PROTECTed while being filled.
  */
+#include <stdlib.h>
+#include <string.h>
+
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
@@ -64,6 +67,63 @@ SEXP gp_approx_L(SEXP l, SEXP lp, SEXP Ls, SEXP dLdls) {
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, n));
   check(gpb200_approx_L(handle(), n, Rf_asReal(l), P, REAL(lp), a, b, REAL(out)), "approx_L");
   UNPROTECT(1);
+  return out;
+}
+
+/* all P tables of a length-scale grid in one batched call -> list(Ls = list(...), dLdls = list(...))
+ * (data block of models/cubic_interpolated_gp.stan:11-12; interpolated_gp.stan:15-21) */
+SEXP gp_rbf_cov_chol_grid(SEXP x1, SEXP lp) {
+  const int n = LENGTH(x1), P = LENGTH(lp);
+  double *L = (double *)R_alloc((size_t)P * n * n, sizeof(double));
+  double *dL = (double *)R_alloc((size_t)P * n * n, sizeof(double));
+  int *info = (int *)R_alloc(P, sizeof(int));
+  check(gpb200_rbf_cov_chol_batched(handle(), n, REAL(x1), P, REAL(lp), L, dL, info), "rbf_cov_chol_grid");
+  for (int q = 0; q < P; q++)
+    if (info[q] > 0) Rf_error("rbf_cov_chol_grid: table %d is not positive definite (pivot %d)", q + 1, info[q]);
+  SEXP Ls = PROTECT(Rf_allocVector(VECSXP, P));
+  SEXP dLs = PROTECT(Rf_allocVector(VECSXP, P));
+  for (int q = 0; q < P; q++) {
+    SEXP a = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+    SEXP b = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+    memcpy(REAL(a), L + (size_t)q * n * n, sizeof(double) * (size_t)n * n);
+    memcpy(REAL(b), dL + (size_t)q * n * n, sizeof(double) * (size_t)n * n);
+    SET_VECTOR_ELT(Ls, q, a);
+    SET_VECTOR_ELT(dLs, q, b);
+    UNPROTECT(2);
+  }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_VECTOR_ELT(out, 0, Ls); SET_VECTOR_ELT(out, 1, dLs);
+  SET_STRING_ELT(nm, 0, Rf_mkChar("Ls")); SET_STRING_ELT(nm, 1, Rf_mkChar("dLdls"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(4);
+  return out;
+}
+
+/* approx_L(M, scale, xt, sigma, l) of models/westbrook.stan:2-30 / bH of spectral_test.R:6-27 */
+SEXP gp_approx_L_basis(SEXP M, SEXP scale, SEXP x, SEXP sigma, SEXP l) {
+  const int n = LENGTH(x), m = Rf_asInteger(M);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, m));
+  check(gpb200_approx_L_basis(handle(), n, m, Rf_asReal(scale), REAL(x), Rf_asReal(sigma), Rf_asReal(l), REAL(out),
+                              n > 0 ? n : 1), "approx_L_basis");
+  UNPROTECT(1);
+  return out;
+}
+
+/* L = chol(cov_exp_quad(x, alpha, rho) + diag_add I) and dL/d(alpha | rho): the latent models' Cholesky
+ * with its tangent (exact_gp.stan:17-25, fit_full_gp.stan:18-26) */
+SEXP gp_se_chol_tangent(SEXP x, SEXP alpha, SEXP rho, SEXP diag_add, SEXP wrt) {
+  const int n = LENGTH(x);
+  SEXP L = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+  SEXP dL = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+  check(gpb200_se_chol_tangent(handle(), n, REAL(x), Rf_asReal(alpha), Rf_asReal(rho), Rf_asReal(diag_add),
+                               Rf_asInteger(wrt), REAL(L), REAL(dL)), "se_chol_tangent");
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_VECTOR_ELT(out, 0, L); SET_VECTOR_ELT(out, 1, dL);
+  SET_STRING_ELT(nm, 0, Rf_mkChar("L")); SET_STRING_ELT(nm, 1, Rf_mkChar("dL"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(4);
   return out;
 }
 
@@ -173,6 +233,8 @@ static const R_CallMethodDef call_methods[] = {
     {"gp_gram_ard", (DL_FUNC)&gp_gram_ard, 4},         {"gp_gram_deriv", (DL_FUNC)&gp_gram_deriv, 7},
     {"gp_potrf", (DL_FUNC)&gp_potrf, 1},               {"gp_lml_grad_draws", (DL_FUNC)&gp_lml_grad_draws, 4},
     {"gp_condition", (DL_FUNC)&gp_condition, 6},       {"gp_cond_mvn", (DL_FUNC)&gp_cond_mvn, 4},
+    {"gp_rbf_cov_chol_grid", (DL_FUNC)&gp_rbf_cov_chol_grid, 2}, {"gp_approx_L_basis", (DL_FUNC)&gp_approx_L_basis, 5},
+    {"gp_se_chol_tangent", (DL_FUNC)&gp_se_chol_tangent, 5},
     {NULL, NULL, 0}};
 
 void R_init_gpb200_r(DllInfo *dll) {

@@ -62,3 +62,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU oracle", ""), os.path.join(dirpath, f)
+
+
+def test_r_shim_type_checks_against_mock_r_api():
+    """R is not installed here, so r/shim.c cannot be built; it is at least type-checked against a mock
+    of the R C API (r/mock/) and the real include/gpb200.h, and every .Call name used by r/R/gpb200.R
+    is registered in the shim."""
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Wno-cast-function-type", "-Werror",
+                           "-I" + os.path.join(ROOT, "r", "mock"), "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "r", "shim.c")])
+    shim = open(os.path.join(ROOT, "r", "shim.c")).read()
+    rfile = open(os.path.join(ROOT, "r", "R", "gpb200.R")).read()
+    registered = set(re.findall(r'\{"(gp_\w+)", \(DL_FUNC\)', shim))
+    called = set(re.findall(r'\.Call\("(gp_\w+)"', rfile))
+    assert called and called <= registered, called - registered
+    # every gpb200_* the shim calls is declared in the header
+    used = set(re.findall(r"\b(gpb200_\w+)\s*\(", shim))
+    assert used <= set(header_symbols()) | {"gpb200_handle_t"}
