@@ -87,7 +87,7 @@ class GpuPanelBackend:
 class BlockCyclicGP:
     """Distributed factorisation and LML of one exact GP with a squared-exponential kernel."""
 
-    def __init__(self, n, panel_cols=1024, backend=None, group=None):
+    def __init__(self, n, panel_cols=512, backend=None, group=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group

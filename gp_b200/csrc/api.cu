@@ -347,7 +347,7 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   gpb200_handle_s *h = new (std::nothrow) gpb200_handle_s();
   if (!h) return -1002;
   h->device = device;
-  if (panel_smem_setup(h)) { delete h; return -1000; }
+  if (panel_smem_setup(h) || gemm_smem_setup(h)) { delete h; return -1000; }
   *out = h;
   return 0;
 }

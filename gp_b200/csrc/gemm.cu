@@ -252,16 +252,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
 
 template <bool A_KC, bool B_KC, int EPI>
 static int launch_one(Handle *h, const GemmParams &p, int ntasks, int batch) {
-  static bool configured = false;
   auto kern = gemm_tile_kernel<A_KC, B_KC, EPI>;
-  if (!configured) {
-    GPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    configured = true;
-  }
   dim3 grid(ntasks, batch);
   ProfScope ps__(h, PC_GEMM);
   kern<<<grid, NTHREADS, GEMM_SMEM_BYTES, h->stream>>>(p);
   GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+// The opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: it is set when a
+// handle is created (gpb200_create), once per handle, so one process may hold handles on several GPUs.
+int gemm_smem_setup(Handle *h) {
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<false, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   return 0;
 }
 

@@ -19,7 +19,7 @@ from gp_b200.block_cyclic import BlockCyclicGP, GpuPanelBackend  # noqa: E402
 
 def main():
     sizes = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [4096, 8192, 16384, 32768]
-    pc = 1024
+    pc = 512
     for a in sys.argv[1:]:
         if a.startswith("--panel="):
             pc = int(a.split("=")[1])
