@@ -24,3 +24,15 @@ def handle():
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "gp_derivs_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def ch2_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ch2_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def westbrook():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "westbrook_xy.npz"))

@@ -86,3 +86,46 @@ def test_headline_n4096_sample(handle):
     lml, grad, info = handle.lml_grad_batched(x, y, th)
     rv, rg = o.lml_grad_lapack(x, y, *th[1])
     assert abs(lml[1] - rv) <= 1e-9 * abs(rv) and relerr(grad[1], rg) < 1e-9
+
+
+def test_reference_ch2_golden_on_gpu(handle, ch2_golden):
+    # the reference's own ch2.py outputs (tests/golden/make_golden_ch2.py): SE Gram in its l2 form,
+    # a 1000-point posterior conditioned on 4 observations, Cholesky of the posterior + 1e-10 I
+    g = ch2_golden
+    a2, rho = float(g["eta2"]), float(np.sqrt(g["l2"] / 2.0))
+    xs, xd, idx = g["xs"], g["xd"], g["idx"]
+    Ksd = handle.gram_outer("QQ", xs, xd, rho, a2)
+    assert relerr(Ksd, g["Ksd"]) < 1e-13
+    Kss = handle.gram_outer("QQ", xs, xs, rho, a2)
+    mu, cov = handle.gp_condition(g["Kdd"], Ksd, Kss, g["f"], 0.0, 0.0)
+    assert relerr(mu, g["m"]) < 1e-9
+    assert np.max(np.abs(cov[np.ix_(idx, idx)] - g["Kt_sub"])) < 1e-9
+    # numerically rank-deficient (cond ~ 1e10 after the jitter): the reference's LAPACK factorisation
+    # succeeds with backward error 1.7e-16; ours must succeed too and be backward stable
+    A = cov + 1e-10 * np.eye(1000)
+    A = 0.5 * (A + A.T)
+    L = handle.potrf(A)
+    assert np.linalg.norm(L @ L.T - A) / np.linalg.norm(A) < 20 * 1000 * EPS
+    assert relerr(np.diag(L)[:5], g["L_diag"][:5]) < 1e-6
+
+
+def test_westbrook_real_inputs(handle, westbrook):
+    # real-data fixture of the reference (discourse_westbrook/westbrook.csv): N = 1438 with only 1073
+    # unique x -> ragged size (pads to 1536) and exactly repeated rows/columns in the Gram matrix
+    x, y = westbrook["x"], westbrook["y"] - westbrook["y"].mean()
+    order = np.argsort(x, kind="stable")
+    x, y = x[order], y[order]
+    for th in ([0.5, 0.2, 0.45], [1.0, 0.05, 0.3]):
+        v, g = handle.lml_grad(x, y, th)
+        rv, rg = o.lml_grad_lapack(x, y, *th)
+        assert abs(v - rv) <= 1e-9 * abs(rv) and relerr(g, rg) < 1e-9
+    # without noise the matrix is singular (exactly repeated rows): the pivot of the first repeated
+    # input is zero up to rounding, so LAPACK reports it (info = 3 here); which later pivot first goes
+    # non-positive is rounding-dependent, only "reported as not positive definite" is asserted
+    K0 = o.gram_se(x, 1.0, 0.3, 0.0)
+    _, info = handle.potrf(K0, raise_on_info=False)
+    assert info >= o.potrf_info(K0) > 0
+    # westbrook_exact.stan:20-21 jitter 1e-12 is below rounding for this matrix; 1e-6 factors and is stable
+    K6 = o.gram_se(x, 1.0, 0.3, 1e-6)
+    L = handle.potrf(K6)
+    assert np.linalg.norm(L @ L.T - K6) / np.linalg.norm(K6) < 20 * 1438 * EPS

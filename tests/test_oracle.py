@@ -161,3 +161,22 @@ def test_latent_gp_reverse_mode_adjoint_matches_finite_differences():
     fd_l = (o.exact_gp_lp_grad(x, y, 0.9 + h, 0.3, z)[0] - o.exact_gp_lp_grad(x, y, 0.9 - h, 0.3, z)[0]) / (2 * h)
     fd_s = (o.exact_gp_lp_grad(x, y, 0.9, 0.3 + h, z)[0] - o.exact_gp_lp_grad(x, y, 0.9, 0.3 - h, z)[0]) / (2 * h)
     assert abs(fd_l - g["l"]) < 1e-6 * abs(g["l"]) and abs(fd_s - g["sigma"]) < 1e-6 * abs(g["sigma"])
+
+
+def test_oracle_matches_reference_ch2_golden(ch2_golden):
+    # the reference's ch2.py:55-91 in its l2 parametrisation: alpha^2 = eta2, rho = sqrt(l2 / 2)
+    g = ch2_golden
+    phi = (float(np.sqrt(g["eta2"])), float(np.sqrt(g["l2"] / 2.0)))
+    xs, xd, idx = g["xs"], g["xd"], g["idx"]
+    assert relerr(o.rk_QQ(xs, xd, phi), g["Ksd"]) < 1e-13
+    assert relerr(o.rk_QQ(xs[idx], xs[idx], phi), g["Kss_sub"]) < 1e-13
+    mu, cov = o.gp_condition(g["Kdd"], g["Ksd"], o.rk_QQ(xs, xs, phi), g["f"], 0.0, 0.0)
+    assert relerr(mu, g["m"]) < 1e-10
+    assert np.max(np.abs(cov[np.ix_(idx, idx)] - g["Kt_sub"])) < 1e-10
+
+
+def test_westbrook_fixture_shape(westbrook):
+    x = westbrook["x"]
+    assert x.shape == (1438,) and len(np.unique(x)) == 1073 and abs(x.min() + 0.4976) < 1e-3 and x.max() == 0.5
+    # duplicated inputs: the exact-GP Gram is singular without jitter (SURVEY 2.1 "Data")
+    assert o.potrf_info(o.gram_se(x, 1.0, 0.3, 0.0)) > 0
