@@ -787,6 +787,7 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
     if (limit < fixed + per_item + 8192) BAD_ARG(h, 1002, "lml_grad_batched: workspace limit too small for one item");
     Bc = (int)std::min<size_t>((size_t)B, (limit - fixed - 8192) / per_item);
   }
+  Bc = std::min(Bc, 65535);  // gridDim.y of the batched launches
   Arena a;
   RC(ws_reserve(h, fixed + per_item * (size_t)Bc + 8192, &a));
 
