@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """The shared library is a build artefact (git-ignored): build it when it is missing or stale so
+    that a fresh checkout can run the suite directly (nvcc cross-compiles without a GPU)."""
+    try:
+        from gp_b200 import build as b
+        b.build()
+    except Exception as e:  # a box without nvcc still runs against a prebuilt .so that travelled with it
+        import warnings
+        warnings.warn("could not (re)build libgpb200.so: %r" % (e,))
+
+
 @pytest.fixture(scope="session")
 def handle():
     from gp_b200 import capi
