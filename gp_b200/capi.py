@@ -33,6 +33,7 @@ SIGNATURES = {
     "gpb200_launch_count": (_ll, [_h]),
     "gpb200_version": (C.c_int, []),
     "gpb200_set_workspace_limit": (C.c_int, [_h, _ll]),
+    "gpb200_graph_replays": (_ll, [_h]),
     "gpb200_set_chol_panel_tiles": (C.c_int, [_h, C.c_int]),
     "gpb200_set_profiling": (C.c_int, [_h, C.c_int]),
     "gpb200_get_profile": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
@@ -173,6 +174,9 @@ class Handle:
         return int(self.lib.gpb200_launch_count(self._h))
 
     PROFILE_CLASSES = ("gemm", "potrf_tile", "trsm_tile", "gram", "solve", "other")
+
+    def graph_replays(self) -> int:
+        return int(self.lib.gpb200_graph_replays(self._h))
 
     def set_chol_panel_tiles(self, tiles: int):
         self._check(self.lib.gpb200_set_chol_panel_tiles(self._h, int(tiles)), "set_chol_panel_tiles")

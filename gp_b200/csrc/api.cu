@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "common.cuh"
@@ -40,6 +41,9 @@ int ws_reserve(Handle *h, size_t bytes, Arena *a) {
   if (bytes > h->ws_bytes) {
     if (h->ws) {
       GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (h->gstream) GPB_CUDA(h, cudaStreamSynchronize(h->gstream));
+      for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);  // they bake in workspace addresses
+      h->graphs.clear();
       GPB_CUDA(h, cudaFree(h->ws));
       h->ws = nullptr;
       h->ws_bytes = 0;
@@ -348,6 +352,11 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (!h) return -1002;
   h->device = device;
   if (panel_smem_setup(h) || gemm_smem_setup(h)) { delete h; return -1000; }
+  if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return -1000; }
+  const char *ng = getenv("GPB200_NO_GRAPH");
+  if (ng && ng[0] == '1') h->graphs_enabled = 0;
   *out = h;
   return 0;
 }
@@ -356,6 +365,10 @@ extern "C" int gpb200_destroy(gpb200_handle_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (h->gstream) { cudaStreamSynchronize(h->gstream); cudaStreamDestroy(h->gstream); }
+  if (h->g_in) cudaEventDestroy(h->g_in);
+  if (h->g_out) cudaEventDestroy(h->g_out);
   if (h->ws) cudaFree(h->ws);
   for (auto &kv : h->task_cache) cudaFree(kv.second.first);
   delete h;
@@ -802,45 +815,103 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
   double *partial = a.take<double>((size_t)Bc * ntasks * 4);
   if (!partial) BAD_ARG(h, 1002, "lml_grad_batched: workspace arithmetic error");
 
-  if (x_stride) RC(to_device_2d(h, x, x_stride, dx, n, n, B)); else RC(to_device(h, x, dx, n));
-  if (y_stride) RC(to_device_2d(h, y, y_stride, dy, n, n, B)); else RC(to_device(h, y, dy, n));
-  RC(to_device(h, theta, dth, (size_t)B * 3));
-  GPB_CUDA(h, cudaMemsetAsync(dinfo, 0, (size_t)B * sizeof(int), h->stream));
-
-  for (int b0 = 0; b0 < B; b0 += Bc) {
-    const int bc = std::min(Bc, B - b0);
-    const double *cx = dx + (long long)b0 * xs, *cy = dy + (long long)b0 * ys, *cth = dth + (long long)b0 * 3;
-    RC(launch_gram_se_batched(h, n, np, cx, xs, cth, jitter, 1, Lbuf, mat, bc));
-    RC(chol_batched(h, Lbuf, np, mat, n, bc, dinfo + b0, nullptr));
-    RC(extract_diag(h, np, Lbuf, mat, dvec, bc));
-    if (want_grad) {
-      RC(trtri_batched(h, Lbuf, Sbuf, np, mat, bc));
-      RC(launch_trmv_lower_n(h, np, Lbuf, mat, cy, ys, n, zbuf, np, bc));
-      RC(launch_trmv_lower_t(h, np, Lbuf, mat, zbuf, np, abuf, np, bc));
-      GemmParams p{};
-      p.A = mref(Lbuf, np, mat);
-      p.B = mref(Lbuf, np, mat);
-      p.C = mref(nullptr, np, mat);
-      p.tasks = tl.at(0);
-      p.x = cx; p.x_stride = xs;
-      p.avec = abuf; p.a_stride = np;
-      p.theta = cth;
-      p.partial = partial;
-      p.n = n;
-      p.ntasks = ntasks;
-      RC(launch_gemm(h, LAYOUT_TN, EPI_TRACE, p, ntasks, bc));
-    } else {
-      RC(launch_tile_inverse(h, Lbuf, Sbuf, np, mat, nt, bc));
-      if (bc >= 32) RC(launch_trsv_blocked(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, np, bc));
-      else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
+  // The kernel sequence (everything between staging the inputs and reading the outputs).
+  auto run_sequence = [&]() -> int {
+    GPB_CUDA(h, cudaMemsetAsync(dinfo, 0, (size_t)B * sizeof(int), h->stream));
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+      const int bc = std::min(Bc, B - b0);
+      const double *cx = dx + (long long)b0 * xs, *cy = dy + (long long)b0 * ys, *cth = dth + (long long)b0 * 3;
+      RC(launch_gram_se_batched(h, n, np, cx, xs, cth, jitter, 1, Lbuf, mat, bc));
+      RC(chol_batched(h, Lbuf, np, mat, n, bc, dinfo + b0, nullptr));
+      RC(extract_diag(h, np, Lbuf, mat, dvec, bc));
+      if (want_grad) {
+        RC(trtri_batched(h, Lbuf, Sbuf, np, mat, bc));
+        RC(launch_trmv_lower_n(h, np, Lbuf, mat, cy, ys, n, zbuf, np, bc));
+        RC(launch_trmv_lower_t(h, np, Lbuf, mat, zbuf, np, abuf, np, bc));
+        GemmParams p{};
+        p.A = mref(Lbuf, np, mat);
+        p.B = mref(Lbuf, np, mat);
+        p.C = mref(nullptr, np, mat);
+        p.tasks = tl.at(0);
+        p.x = cx; p.x_stride = xs;
+        p.avec = abuf; p.a_stride = np;
+        p.theta = cth;
+        p.partial = partial;
+        p.n = n;
+        p.ntasks = ntasks;
+        RC(launch_gemm(h, LAYOUT_TN, EPI_TRACE, p, ntasks, bc));
+      } else {
+        RC(launch_tile_inverse(h, Lbuf, Sbuf, np, mat, nt, bc));
+        if (bc >= 32) RC(launch_trsv_blocked(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, np, bc));
+        else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
+      }
+      RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
     }
-    RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
+    return 0;
+  };
+
+  // Small problems are launch-latency bound (tens of launches of a few microseconds each): replay
+  // them as one CUDA graph on the handle's own stream, ordered against the caller's stream by events.
+  const bool use_graph = h->graphs_enabled && !h->profiling && Bc == B && nt <= 16 && (long long)B * nt * nt <= 4096;
+  cudaStream_t user_stream = h->stream;
+  if (use_graph) {
+    GPB_CUDA(h, cudaEventRecord(h->g_in, user_stream));
+    GPB_CUDA(h, cudaStreamWaitEvent(h->gstream, h->g_in, 0));
+    h->stream = h->gstream;
   }
-  RC(from_device(h, dlml, lml, (size_t)B * sizeof(double)));
-  if (want_grad && grad) RC(from_device(h, dgrad, grad, (size_t)B * 3 * sizeof(double)));
-  if (info) RC(from_device(h, dinfo, info, (size_t)B * sizeof(int)));
-  return finish(h);
+  int rc = 0;
+  do {
+    if (x_stride) rc = to_device_2d(h, x, x_stride, dx, n, n, B); else rc = to_device(h, x, dx, n);
+    if (rc) break;
+    if (y_stride) rc = to_device_2d(h, y, y_stride, dy, n, n, B); else rc = to_device(h, y, dy, n);
+    if (rc) break;
+    if ((rc = to_device(h, theta, dth, (size_t)B * 3))) break;
+    if (!use_graph) {
+      rc = run_sequence();
+    } else {
+      long long jbits;
+      memcpy(&jbits, &jitter, sizeof(jbits));
+      const std::vector<long long> key = {n, B, want_grad, xs, ys, jbits, (long long)(uintptr_t)h->ws, h->chol_panel_override};
+      auto it = h->graphs.find(key);
+      if (it == h->graphs.end()) {
+        // task lists allocate and synchronise on first use: make sure they exist before the capture
+        TaskList t1, t2, t3;
+        const int pt = h->chol_panel_override > 0 ? std::min(nt, h->chol_panel_override) : chol_panel_tiles(nt, B);
+        if ((rc = tasks_chol(h, nt, pt, &t1, &t2))) break;
+        if (nt > 1 && (rc = tasks_trtri(h, nt, &t1, &t3))) break;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = -1000; break; }
+        const long long before = h->launches;
+        rc = run_sequence();
+        const cudaError_t ce = cudaStreamEndCapture(h->gstream, &graph);
+        if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) rc = -1000; break; }
+        cudaGraphExec_t exec = nullptr;
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); rc = -1000; break; }
+        cudaGraphDestroy(graph);
+        it = h->graphs.emplace(key, Handle::GraphEntry{exec, h->launches - before}).first;
+        h->launches = before;  // counted per replay below
+      }
+      if (cudaGraphLaunch(it->second.exec, h->gstream) != cudaSuccess) { rc = -1001; break; }
+      h->launches += it->second.nodes;
+      h->graph_replays++;
+    }
+    if (rc) break;
+    if ((rc = from_device(h, dlml, lml, (size_t)B * sizeof(double)))) break;
+    if (want_grad && grad && (rc = from_device(h, dgrad, grad, (size_t)B * 3 * sizeof(double)))) break;
+    if (info && (rc = from_device(h, dinfo, info, (size_t)B * sizeof(int)))) break;
+    rc = finish(h);
+  } while (0);
+  if (use_graph) {
+    h->stream = user_stream;
+    cudaEventRecord(h->g_out, h->gstream);
+    cudaStreamWaitEvent(user_stream, h->g_out, 0);
+  }
+  if (rc && !h->err[0]) snprintf(h->err, sizeof(h->err), "lml_grad_batched: CUDA graph path failed (%d)", rc);
+  return rc;
 }
+
+// number of CUDA-graph replays so far (small evaluations are replayed as one graph)
+extern "C" long long gpb200_graph_replays(gpb200_handle_t h) { return h ? h->graph_replays : 0; }
 
 extern "C" int gpb200_lml_grad(gpb200_handle_t h, int n, const double *x, const double *y, const double *theta,
                                double jitter, double *lml, double *grad) {

@@ -56,6 +56,15 @@ struct Handle {
   size_t ws_bytes = 0;
   // cached device-side task lists keyed by (kind, nt)
   std::map<long long, std::pair<TileTask *, std::vector<int>>> task_cache;
+  // CUDA graphs of the launch sequence of small (launch-latency-bound) LML evaluations, keyed by the
+  // problem signature; replayed on a handle-owned stream (the caller's stream may be the legacy
+  // default stream, which cannot be captured).  Invalidated when the workspace moves.
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t g_in = nullptr, g_out = nullptr;
+  struct GraphEntry { cudaGraphExec_t exec; long long nodes; };
+  std::map<std::vector<long long>, GraphEntry> graphs;
+  int graphs_enabled = 1;
+  long long graph_replays = 0;
   // optional per-kernel-class timing with CUDA events on the handle's stream (bench.py roofline)
   int profiling = 0;
   struct ProfRec { int cls; cudaEvent_t e0, e1; };

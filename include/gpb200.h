@@ -48,6 +48,10 @@ GPB200_API int gpb200_version(void);
  * a batch that does not fit is processed in chunks with identical results */
 GPB200_API int gpb200_set_workspace_limit(gpb200_handle_t h, long long bytes);
 
+/* Small (launch-latency-bound) lml_grad evaluations are replayed as one CUDA graph; this returns how
+ * many replays the handle has done.  GPB200_NO_GRAPH=1 in the environment disables the graphs. */
+GPB200_API long long gpb200_graph_replays(gpb200_handle_t h);
+
 /* tuning/testing knob: Cholesky panel width in 128-column tiles (0 = automatic: pure left-looking
  * for batches >= 64, 8-tile panels + right-looking trailing updates for small batches) */
 GPB200_API int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles);
