@@ -41,6 +41,17 @@ inline void eval(const std::vector<double>& x, const Eigen::VectorXd& y, double 
 }
 }  // namespace gpb200_stan
 
+namespace gpb200_stan {
+// operands that are `var` contribute a partial; `double` arguments contribute nothing (C++11 overloads,
+// no `if constexpr`: the rstan toolchains of the reference's era compile as C++11/14)
+inline void add_operand(std::vector<stan::math::var>& ops, std::vector<double>& partials, const stan::math::var& v,
+                        double g) {
+  ops.push_back(v);
+  partials.push_back(g);
+}
+inline void add_operand(std::vector<stan::math::var>&, std::vector<double>&, double, double) {}
+}  // namespace gpb200_stan
+
 // reverse-mode overload: any of alpha, rho, sigma may be var
 template <typename T0__, typename T1__, typename T2__>
 typename boost::math::tools::promote_args<T0__, T1__, T2__>::type
@@ -51,9 +62,9 @@ gp_lml(const std::vector<double>& x, const Eigen::Matrix<double, Eigen::Dynamic,
   gpb200_stan::eval(x, y, value_of(alpha), value_of(rho), value_of(sigma), lml, g);
   std::vector<stan::math::var> operands;
   std::vector<double> partials;
-  if (!stan::is_constant<T0__>::value) { operands.push_back(alpha); partials.push_back(g[0]); }
-  if (!stan::is_constant<T1__>::value) { operands.push_back(rho); partials.push_back(g[1]); }
-  if (!stan::is_constant<T2__>::value) { operands.push_back(sigma); partials.push_back(g[2]); }
+  gpb200_stan::add_operand(operands, partials, alpha, g[0]);
+  gpb200_stan::add_operand(operands, partials, rho, g[1]);
+  gpb200_stan::add_operand(operands, partials, sigma, g[2]);
   return stan::math::precomputed_gradients(lml, operands, partials);
 }
 

@@ -1,0 +1,7 @@
+// type-checks stan/gp_lml_stan.hpp against the mock: both overloads must instantiate
+#include "stan/math.hpp"
+#include "../gp_lml_stan.hpp"
+using stan::math::var;
+var f1(const std::vector<double> &x, const Eigen::VectorXd &y, var a, var r, var s) { return gp_lml(x, y, a, r, s, nullptr); }
+var f2(const std::vector<double> &x, const Eigen::VectorXd &y, double a, var r, double s) { return gp_lml(x, y, a, r, s, nullptr); }
+double f3(const std::vector<double> &x, const Eigen::VectorXd &y) { return gp_lml(x, y, 1.0, 1.0, 0.3, nullptr); }

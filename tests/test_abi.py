@@ -79,3 +79,11 @@ def test_r_shim_type_checks_against_mock_r_api():
     # every gpb200_* the shim calls is declared in the header
     used = set(re.findall(r"\b(gpb200_\w+)\s*\(", shim))
     assert used <= set(header_symbols()) | {"gpb200_handle_t"}
+
+
+def test_stan_header_type_checks_against_mock_stan():
+    """Stan Math / Eigen are absent, so stan/gp_lml_stan.hpp cannot be built into a model here; it is
+    type-checked as C++11 (the reference era's rstan toolchain) against a minimal mock of the names
+    it uses (stan/mock/), for all-var, mixed and all-double argument lists."""
+    subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "stan", "mock"),
+                           os.path.join(ROOT, "stan", "mock", "check.cpp")])

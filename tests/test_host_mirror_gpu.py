@@ -188,3 +188,23 @@ def test_eigen_basis_approx_L(handle):
     Lr = o.approx_L_basis(20, 0.25, x, 1.0, 0.4)
     ref20 = np.log10(np.max(np.abs(o.cov_exp_quad(x, 1.0, 0.4) - Lr @ Lr.T)) + 1e-20)
     assert e20 < e10 < 0 and abs(e20 - ref20) < 1e-6
+
+
+def test_map_fit_recovers_noise_level(handle):
+    # the caller of the hot path (CS-A): maximise lp__ of fit_hyperparameters.stan with GPU value+gradient
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("fit_example", os.path.join(os.path.dirname(__file__), "..", "examples",
+                                                                              "fit_hyperparameters.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    rng = np.random.default_rng(1)
+    t = np.linspace(0, 10, 300)
+    y = np.sin(1.3 * t) + 0.15 * rng.standard_normal(300)
+    rho, alpha, sigma, lp, nit = mod.fit(t, y, handle=handle)
+    assert 0.10 < sigma < 0.20 and 0.5 < rho < 3.0 and 0.3 < alpha < 3.0
+    # a stationary point of the oracle's lp__ as well
+    u = np.log([rho, alpha, sigma])
+    h = 1e-5
+    for k in range(3):
+        up, um = u.copy(), u.copy(); up[k] += h; um[k] -= h
+        fd = (o.lp_fit_hyperparameters(t, y, *up) - o.lp_fit_hyperparameters(t, y, *um)) / (2 * h)
+        assert abs(fd) < 5e-2
