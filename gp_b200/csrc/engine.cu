@@ -1,0 +1,277 @@
+// Host-side engines of libgpb200: workspace arena, tile task lists and the tiled algorithms built
+// from the DMMA GEMM and the panel kernels (left-looking batched Cholesky with an optional
+// right-looking panel split, in-place recursive triangular inverse).  No C-ABI entry points here.
+#include "host.cuh"
+
+namespace gpb {
+
+// ---------------------------------------------------------------------------------------------
+// workspace arena
+// ---------------------------------------------------------------------------------------------
+
+
+int ws_reserve(Handle *h, size_t bytes, Arena *a) {
+  if (bytes > h->ws_bytes) {
+    if (h->ws) {
+      GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (h->gstream) GPB_CUDA(h, cudaStreamSynchronize(h->gstream));
+      for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);  // they bake in workspace addresses
+      h->graphs.clear();
+      GPB_CUDA(h, cudaFree(h->ws));
+      h->ws = nullptr;
+      h->ws_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&h->ws, bytes);
+    if (e != cudaSuccess) {
+      snprintf(h->err, sizeof(h->err), "workspace allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return -1002;
+    }
+    h->ws_bytes = bytes;
+  }
+  a->base = reinterpret_cast<char *>(h->ws);
+  a->cap = h->ws_bytes;
+  a->off = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// task lists (host-built once per tile count, cached on the device)
+// ---------------------------------------------------------------------------------------------
+
+
+int upload_tasks(Handle *h, long long key, const std::vector<TileTask> &tasks, const std::vector<int> &offsets,
+                 TaskList *out) {
+  auto it = h->task_cache.find(key);
+  if (it == h->task_cache.end()) {
+    TileTask *dev = nullptr;
+    const size_t bytes = std::max<size_t>(tasks.size(), 1) * sizeof(TileTask);
+    GPB_CUDA(h, cudaMalloc(&dev, bytes));
+    if (!tasks.empty())
+      GPB_CUDA(h, cudaMemcpyAsync(dev, tasks.data(), tasks.size() * sizeof(TileTask), cudaMemcpyHostToDevice, h->stream));
+    GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    it = h->task_cache.emplace(key, std::make_pair(dev, offsets)).first;
+  }
+  out->dev = it->second.first;
+  out->offsets = &it->second.second;
+  return 0;
+}
+
+bool cached(Handle *h, long long key, TaskList *out) {
+  auto it = h->task_cache.find(key);
+  if (it == h->task_cache.end()) return false;
+  out->dev = it->second.first;
+  out->offsets = &it->second.second;
+  return true;
+}
+
+
+void sort_desc(std::vector<TileTask> &v, size_t from) {
+  std::stable_sort(v.begin() + from, v.end(), [](const TileTask &x, const TileTask &y) { return x.k_len > y.k_len; });
+}
+
+// Cholesky task lists.  Panels of `pt` tile columns: inside a panel the factorisation is
+// left-looking (step j updates block column j with the panel's columns to its left, K = (j-p0)*128);
+// after a panel is complete one right-looking launch applies it to everything to its right
+// (K = pt*128).  pt = nt is the pure left-looking algorithm used for large batches; a narrow panel
+// gives a single large matrix enough tiles per launch to fill 148 SMs.
+int tasks_chol(Handle *h, int nt, int pt, TaskList *upd, TaskList *trail) {
+  const long long k1 = tkey(TK_CHOL, nt, pt), k2 = tkey(TK_CHOL_TRAIL, nt, pt);
+  if (cached(h, k1, upd) && cached(h, k2, trail)) return 0;
+  std::vector<TileTask> t, tt;
+  std::vector<int> off(1, 0), offt(1, 0);
+  for (int j = 0; j < nt; j++) {
+    const int p0 = (j / pt) * pt;
+    if (j > p0)
+      for (int i = j; i < nt; i++)
+        t.push_back({i * TILE, p0 * TILE, j * TILE, p0 * TILE, i * TILE, j * TILE, (j - p0) * TILE, i == j});
+    off.push_back((int)t.size());
+  }
+  for (int p0 = 0; p0 < nt; p0 += pt) {
+    const int p1 = std::min(nt, p0 + pt);
+    for (int jj = p1; jj < nt; jj++)
+      for (int i = jj; i < nt; i++)
+        tt.push_back({i * TILE, p0 * TILE, jj * TILE, p0 * TILE, i * TILE, jj * TILE, (p1 - p0) * TILE, i == jj});
+    offt.push_back((int)tt.size());
+  }
+  int rc = upload_tasks(h, k1, t, off, upd);
+  if (rc) return rc;
+  return upload_tasks(h, k2, tt, offt, trail);
+}
+
+struct Node { int lo, mid, hi, level; };
+int build_nodes(int lo, int hi, std::vector<Node> &nodes) {
+  if (hi - lo <= 1) return 0;
+  const int mid = lo + (hi - lo + 1) / 2;
+  const int l1 = build_nodes(lo, mid, nodes), l2 = build_nodes(mid, hi, nodes);
+  const int lvl = std::max(l1, l2) + 1;
+  nodes.push_back({lo, mid, hi, lvl});
+  return lvl;
+}
+
+// in-place recursive inverse of the lower-triangular factor: per node
+//   S   = W22 * L21          (scratch buffer)        S[i,j] = sum_{k=mid..i} W[i,k] L[k,j]
+//   W21 = -S * W11           (over L21 in place)     W[i,j] = -sum_{k=j..mid-1} S[i,k] W[k,j]
+int tasks_trtri(Handle *h, int nt, TaskList *s_out, TaskList *w_out) {
+  const long long ks = tkey(TK_TRTRI_S, nt), kw = tkey(TK_TRTRI_W, nt);
+  if (cached(h, ks, s_out) && cached(h, kw, w_out)) return 0;
+  std::vector<Node> nodes;
+  const int top = build_nodes(0, nt, nodes);
+  std::vector<TileTask> ts, tw;
+  std::vector<int> os(1, 0), ow(1, 0);
+  for (int lvl = 1; lvl <= top; lvl++) {
+    const size_t fs = ts.size(), fw = tw.size();
+    for (const Node &nd : nodes) {
+      if (nd.level != lvl) continue;
+      for (int i = nd.mid; i < nd.hi; i++)
+        for (int j = nd.lo; j < nd.mid; j++) {
+          ts.push_back({i * TILE, nd.mid * TILE, nd.mid * TILE, j * TILE, i * TILE, j * TILE, (i - nd.mid + 1) * TILE, 0});
+          tw.push_back({i * TILE, j * TILE, j * TILE, j * TILE, i * TILE, j * TILE, (nd.mid - j) * TILE, 0});
+        }
+    }
+    sort_desc(ts, fs);
+    sort_desc(tw, fw);
+    os.push_back((int)ts.size());
+    ow.push_back((int)tw.size());
+  }
+  int rc = upload_tasks(h, ks, ts, os, s_out);
+  if (rc) return rc;
+  return upload_tasks(h, kw, tw, ow, w_out);
+}
+
+// G = W^T W, lower tiles: G[i,j] = sum_{k>=i} W[k,i]^T W[k,j]
+int tasks_lauum(Handle *h, int nt, TaskList *out) {
+  const long long key = tkey(TK_LAUUM, nt);
+  if (cached(h, key, out)) return 0;
+  std::vector<TileTask> t;
+  for (int i = 0; i < nt; i++)
+    for (int j = 0; j <= i; j++) t.push_back({i * TILE, i * TILE, i * TILE, j * TILE, i * TILE, j * TILE, (nt - i) * TILE, i == j});
+  sort_desc(t, 0);
+  std::vector<int> off = {0, (int)t.size()};
+  return upload_tasks(h, key, t, off, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// engines on padded device buffers
+// ---------------------------------------------------------------------------------------------
+
+// Batched tiled Cholesky, in place on Lbuf (np x np per item, lower tiles valid on entry).
+// Panel width: pure left-looking when the batch alone fills the GPU, 8-tile (1024-column) panels
+// with right-looking trailing updates otherwise.
+int chol_panel_tiles(int nt, int batch) {
+  if (batch >= 64 || nt <= 8) return nt;
+  return 8;
+}
+
+int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev, double *dvec) {
+  const int nt = np / TILE;
+  const int pt = h->chol_panel_override > 0 ? std::min(nt, h->chol_panel_override) : chol_panel_tiles(nt, batch);
+  TaskList tl, tr;
+  int rc = tasks_chol(h, nt, pt, &tl, &tr);
+  if (rc) return rc;
+  GemmParams p{};
+  p.A = mref(Lbuf, np, stride);
+  p.B = mref(Lbuf, np, stride);
+  p.C = mref(Lbuf, np, stride);
+  p.C0 = mref(Lbuf, np, stride);
+  p.alpha = -1.0;
+  p.beta = 1.0;
+  for (int j = 0; j < nt; j++) {
+    if (tl.count(j) > 0) {
+      p.tasks = tl.at(j);
+      rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(j), batch);
+      if (rc) return rc;
+    }
+    rc = launch_potrf_tile(h, Lbuf, np, stride, j, n, batch, info_dev);
+    if (rc) return rc;
+    rc = launch_trsm_tiles(h, Lbuf, np, stride, j, nt - 1 - j, batch);
+    if (rc) return rc;
+    if ((j + 1) % pt == 0 && j + 1 < nt) {
+      const int panel = j / pt;
+      p.tasks = tr.at(panel);
+      rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tr.count(panel), batch);
+      if (rc) return rc;
+    }
+  }
+  (void)dvec;
+  return 0;
+}
+
+// In-place inverse of the lower-triangular factor held in Lbuf; Sbuf is same-shaped scratch.
+int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long stride, int batch) {
+  const int nt = np / TILE;
+  int rc = launch_tile_inverse(h, Lbuf, Lbuf, np, stride, nt, batch);
+  if (rc) return rc;
+  if (nt == 1) return 0;
+  TaskList ts, tw;
+  rc = tasks_trtri(h, nt, &ts, &tw);
+  if (rc) return rc;
+  for (int lvl = 0; lvl < ts.steps(); lvl++) {
+    GemmParams p{};
+    p.A = mref(Lbuf, np, stride);
+    p.B = mref(Lbuf, np, stride);
+    p.C = mref(Sbuf, np, stride);
+    p.alpha = 1.0;
+    p.beta = 0.0;
+    p.tasks = ts.at(lvl);
+    rc = launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, ts.count(lvl), batch);
+    if (rc) return rc;
+    GemmParams q{};
+    q.A = mref(Sbuf, np, stride);
+    q.B = mref(Lbuf, np, stride);
+    q.C = mref(Lbuf, np, stride);
+    q.alpha = -1.0;
+    q.beta = 0.0;
+    q.tasks = tw.at(lvl);
+    rc = launch_gemm(h, LAYOUT_NN, EPI_AXPBY, q, tw.count(lvl), batch);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+__global__ void extract_diag_kernel(int np, const double *__restrict__ L, long long stride, double *__restrict__ dvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) dvec[(long long)blockIdx.y * np + i] = L[(long long)blockIdx.y * stride + i + (long long)i * np];
+}
+
+int extract_diag(Handle *h, int np, const double *L, long long stride, double *dvec, int batch) {
+  dim3 grid((np + 255) / 256, batch);
+  ProfScope ps__(h, PC_OTHER);
+  extract_diag_kernel<<<grid, 256, 0, h->stream>>>(np, L, stride, dvec);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+// host<->device staging helpers -----------------------------------------------------------------
+int to_device(Handle *h, const double *src, double *dev, size_t count) {
+  GPB_CUDA(h, cudaMemcpyAsync(dev, src, count * sizeof(double), h->device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+int from_device(Handle *h, const void *dev, void *dst, size_t bytes) {
+  GPB_CUDA(h, cudaMemcpyAsync(dst, dev, bytes, h->device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+int to_device_2d(Handle *h, const double *src, long long lds, double *dev, long long ldd, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  GPB_CUDA(h, cudaMemcpy2DAsync(dev, ldd * sizeof(double), src, lds * sizeof(double), rows * sizeof(double), cols,
+                               h->device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+int from_device_2d(Handle *h, const double *dev, long long lds, double *dst, long long ldd, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  GPB_CUDA(h, cudaMemcpy2DAsync(dst, ldd * sizeof(double), dev, lds * sizeof(double), rows * sizeof(double), cols,
+                               h->device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+int finish(Handle *h) {
+  if (!h->device_ptrs) GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int read_info(Handle *h, const int *info_dev, int *out) {
+  GPB_CUDA(h, cudaMemcpyAsync(out, info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // namespace gpb
