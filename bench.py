@@ -319,7 +319,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_evals = 4
+        n_evals = 8
         v, dt, out = cpu_reference_evals_per_sec(n_evals, threads)
         # the timed GPU results must equal the oracle's on the same draws (1e-9 relative)
         for b in range(n_evals):
