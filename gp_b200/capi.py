@@ -35,6 +35,7 @@ SIGNATURES = {
     "gpb200_set_workspace_limit": (C.c_int, [_h, _ll]),
     "gpb200_graph_replays": (_ll, [_h]),
     "gpb200_set_chol_panel_tiles": (C.c_int, [_h, C.c_int]),
+    "gpb200_set_gemm_config": (C.c_int, [_h, C.c_int]),
     "gpb200_set_profiling": (C.c_int, [_h, C.c_int]),
     "gpb200_get_profile": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
     "gpb200_kernel_eval": (C.c_int, [_h, C.c_int, _ll, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
@@ -180,6 +181,9 @@ class Handle:
 
     def set_chol_panel_tiles(self, tiles: int):
         self._check(self.lib.gpb200_set_chol_panel_tiles(self._h, int(tiles)), "set_chol_panel_tiles")
+
+    def set_gemm_config(self, cfg: int):
+        self._check(self.lib.gpb200_set_gemm_config(self._h, int(cfg)), "set_gemm_config")
 
     def set_profiling(self, on: bool):
         self._check(self.lib.gpb200_set_profiling(self._h, int(bool(on))), "set_profiling")

@@ -78,6 +78,13 @@ extern "C" int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles) {
   return 0;
 }
 
+// test/tuning knob: 0 automatic, 1 force the 8-warp GEMM configuration, 2 force the 16-warp zero-skipping one
+extern "C" int gpb200_set_gemm_config(gpb200_handle_t h, int cfg) {
+  if (!h || cfg < 0 || cfg > 2) return -1;
+  h->gemm_cfg_override = cfg;
+  return 0;
+}
+
 extern "C" int gpb200_set_profiling(gpb200_handle_t h, int on) {
   if (!h) return -1;
   h->profiling = on ? 1 : 0;
@@ -326,6 +333,7 @@ int solve_common(Handle *h, int n, int nrhs, const double *L, int ldl, double *B
   TaskList t1;
   RC(tasks_mul(h, TK_MUL_WB, nt, rt, &t1));
   GemmParams p{};
+  p.small_k = gemm_small_k(np);
   p.A = mref(Lbuf, np, 0);
   p.B = mref(B0, np, 0);
   p.C = mref(B1, np, 0);
@@ -337,6 +345,7 @@ int solve_common(Handle *h, int n, int nrhs, const double *L, int ldl, double *B
     TaskList t2;
     RC(tasks_mul(h, TK_MUL_WTB, nt, rt, &t2));
     GemmParams q{};
+    q.small_k = gemm_small_k(np);
     q.A = mref(Lbuf, np, 0);
     q.B = mref(B1, np, 0);
     q.C = mref(B0, np, 0);

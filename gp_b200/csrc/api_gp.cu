@@ -68,6 +68,7 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
         RC(launch_trmv_lower_n(h, np, Lbuf, mat, cy, ys, n, zbuf, np, bc));
         RC(launch_trmv_lower_t(h, np, Lbuf, mat, zbuf, np, abuf, np, bc));
         GemmParams p{};
+        p.small_k = gemm_small_k(np);
         p.A = mref(Lbuf, np, mat);
         p.B = mref(Lbuf, np, mat);
         p.C = mref(nullptr, np, mat);
@@ -181,11 +182,11 @@ int tasks_tangent(Handle *h, int nt, TaskList *t1, TaskList *ta, TaskList *tl) {
   for (int i = 0; i < nt; i++)
     for (int j = 0; j <= i; j++) {
       // T1[i,j] = sum_{k<=i} W[i,k] Kdot[k,j]                       (NN)
-      v1.push_back({i * TILE, 0, 0, j * TILE, i * TILE, j * TILE, (i + 1) * TILE, 0});
+      v1.push_back({i * TILE, 0, 0, j * TILE, i * TILE, j * TILE, (i + 1) * TILE, TF_A_TRI_LAST});
       // A[i,j]  = sum_{k<=j} T1[i,k] W[j,k]                          (NT)
-      v2.push_back({i * TILE, 0, j * TILE, 0, i * TILE, j * TILE, (j + 1) * TILE, 0});
+      v2.push_back({i * TILE, 0, j * TILE, 0, i * TILE, j * TILE, (j + 1) * TILE, TF_B_TRI_LAST});
       // Ldot[i,j] = sum_{k=j..i} L[i,k] Phi[k,j]                     (NN)
-      v3.push_back({i * TILE, j * TILE, j * TILE, j * TILE, i * TILE, j * TILE, (i - j + 1) * TILE, 0});
+      v3.push_back({i * TILE, j * TILE, j * TILE, j * TILE, i * TILE, j * TILE, (i - j + 1) * TILE, TF_A_TRI_LAST | TF_B_TRI_FIRST});
     }
   sort_desc(v1, 0); sort_desc(v2, 0); sort_desc(v3, 0);
   std::vector<int> o1 = {0, (int)v1.size()}, o2 = {0, (int)v2.size()}, o3 = {0, (int)v3.size()};
@@ -223,17 +224,20 @@ int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, const 
   RC(tasks_tangent(h, nt, &t1, &ta, &tl));
   {  // T1 = W Kdot  -> Sbuf (lower tiles)
     GemmParams p{};
+    p.small_k = gemm_small_k(np);
     p.A = mref(Lbuf, np, st); p.B = mref(Dbuf, np, st); p.C = mref(Sbuf, np, st); p.alpha = 1.0; p.tasks = t1.at(0);
     RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, t1.count(0), P));
   }
   {  // A = T1 W^T -> Dbuf (lower tiles)
     GemmParams p{};
+    p.small_k = gemm_small_k(np);
     p.A = mref(Sbuf, np, st); p.B = mref(Lbuf, np, st); p.C = mref(Dbuf, np, st); p.alpha = 1.0; p.tasks = ta.at(0);
     RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, ta.count(0), P));
   }
   RC(launch_phi_lower(h, np, Dbuf, st, P));
   {  // Ldot = L Phi(A) -> Sbuf (lower tiles)
     GemmParams p{};
+    p.small_k = gemm_small_k(np);
     p.A = mref(Lkeep, np, st); p.B = mref(Dbuf, np, st); p.C = mref(Sbuf, np, st); p.alpha = 1.0; p.tasks = tl.at(0);
     RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, tl.count(0), P));
   }
@@ -387,11 +391,13 @@ int condition_device(Handle *h, Arena &a, int n, int m, const double *K, long lo
   RC(tasks_cond(h, np / TILE, mp / TILE, &tv, &tc));
   {
     GemmParams p{};
+    p.small_k = gemm_small_k(np);
     p.A = mref(Lbuf, np, 0); p.B = mref(Ksp, mp, 0); p.C = mref(V, np, 0); p.alpha = 1.0; p.tasks = tv.at(0);
     RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tv.count(0), 1));
   }
   {
     GemmParams p{};
+    p.small_k = gemm_small_k(np);
     p.A = mref(V, np, 0); p.B = mref(V, np, 0); p.C = mref(Cp, mp, 0); p.C0 = mref(Cp, mp, 0);
     p.alpha = -1.0; p.beta = 1.0; p.tasks = tc.at(0);
     RC(launch_gemm(h, LAYOUT_TN, EPI_AXPBY, p, tc.count(0), 1));

@@ -21,8 +21,16 @@ struct TileTask {
   int b_r, b_c;  // start of the B operand
   int c_r, c_c;  // output tile origin
   int k_len;     // contraction length (multiple of 16)
-  int flags;     // bit0: diagonal tile of a symmetric result (trace epilogue weight 1 instead of 2)
+  int flags;     // TF_* bits
 };
+// task flags: bit0 = diagonal tile of a symmetric result (trace epilogue weight 1 instead of 2); the
+// others mark a triangular operand tile at the first / last 128 of the k-range, so that warps whose
+// sub-tile only meets its zero half skip those chunks
+enum { TF_DIAG = 1,
+       TF_A_TRI_FIRST = 2,   // first k-tile of A is zero where k_local < m_local
+       TF_A_TRI_LAST = 4,    // last  k-tile of A is zero where k_local > m_local
+       TF_B_TRI_FIRST = 8,   // first k-tile of B is zero where k_local < n_local
+       TF_B_TRI_LAST = 16 }; // last  k-tile of B is zero where k_local > n_local
 
 struct MatRef {
   double *p;
@@ -41,6 +49,7 @@ struct GemmParams {
   double *partial;                           // B x ntasks x 4
   int n;                                     // true matrix size (mask for the padding)
   int ntasks;
+  int small_k;                               // 1: short k-loops -> 16-warp zero-skipping GEMM configuration
 };
 
 struct Handle {
@@ -50,6 +59,7 @@ struct Handle {
   long long launches = 0;
   long long ws_limit = 0;
   int chol_panel_override = 0;
+  int gemm_cfg_override = 0;  // 0 auto, 1 force the 8-warp configuration, 2 force the 16-warp zero-skipping one
   char err[512] = {0};
   // grow-only device workspace
   void *ws = nullptr;

@@ -125,8 +125,8 @@ int tasks_trtri(Handle *h, int nt, TaskList *s_out, TaskList *w_out) {
       if (nd.level != lvl) continue;
       for (int i = nd.mid; i < nd.hi; i++)
         for (int j = nd.lo; j < nd.mid; j++) {
-          ts.push_back({i * TILE, nd.mid * TILE, nd.mid * TILE, j * TILE, i * TILE, j * TILE, (i - nd.mid + 1) * TILE, 0});
-          tw.push_back({i * TILE, j * TILE, j * TILE, j * TILE, i * TILE, j * TILE, (nd.mid - j) * TILE, 0});
+          ts.push_back({i * TILE, nd.mid * TILE, nd.mid * TILE, j * TILE, i * TILE, j * TILE, (i - nd.mid + 1) * TILE, TF_A_TRI_LAST});
+          tw.push_back({i * TILE, j * TILE, j * TILE, j * TILE, i * TILE, j * TILE, (nd.mid - j) * TILE, TF_B_TRI_FIRST});
         }
     }
     sort_desc(ts, fs);
@@ -145,7 +145,9 @@ int tasks_lauum(Handle *h, int nt, TaskList *out) {
   if (cached(h, key, out)) return 0;
   std::vector<TileTask> t;
   for (int i = 0; i < nt; i++)
-    for (int j = 0; j <= i; j++) t.push_back({i * TILE, i * TILE, i * TILE, j * TILE, i * TILE, j * TILE, (nt - i) * TILE, i == j});
+    for (int j = 0; j <= i; j++)
+      t.push_back({i * TILE, i * TILE, i * TILE, j * TILE, i * TILE, j * TILE, (nt - i) * TILE,
+                   TF_A_TRI_FIRST | (i == j ? (TF_DIAG | TF_B_TRI_FIRST) : 0)});
   sort_desc(t, 0);
   std::vector<int> off = {0, (int)t.size()};
   return upload_tasks(h, key, t, off, out);
@@ -170,6 +172,7 @@ int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int b
   int rc = tasks_chol(h, nt, pt, &tl, &tr);
   if (rc) return rc;
   GemmParams p{};
+  p.small_k = gemm_small_k(np);
   p.A = mref(Lbuf, np, stride);
   p.B = mref(Lbuf, np, stride);
   p.C = mref(Lbuf, np, stride);
@@ -208,6 +211,7 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
   if (rc) return rc;
   for (int lvl = 0; lvl < ts.steps(); lvl++) {
     GemmParams p{};
+    p.small_k = gemm_small_k(np);
     p.A = mref(Lbuf, np, stride);
     p.B = mref(Lbuf, np, stride);
     p.C = mref(Sbuf, np, stride);
@@ -217,6 +221,7 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
     rc = launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, ts.count(lvl), batch);
     if (rc) return rc;
     GemmParams q{};
+    q.small_k = gemm_small_k(np);
     q.A = mref(Sbuf, np, stride);
     q.B = mref(Lbuf, np, stride);
     q.C = mref(Lbuf, np, stride);

@@ -23,11 +23,27 @@ namespace gpb {
 
 constexpr int KC = 16;
 constexpr int STAGES = 4;
-constexpr int NTHREADS = 256;
+// Two configurations of the same kernel are built:
+//   Big   2x4 warps of 64x32, no zero-skipping       -- long k-loops (nt > 12): fewest fragment loads per DMMA
+//   Small 4x4 warps of 32x32, triangular zero-skip   -- short k-loops, where the diagonal tiles of
+//         triangular operands are a large share of the work (19 % of the executed flops at N=1024)
+template <int WARPS_M_, int WARPS_N_, bool SKIP_>
+struct GemmCfg {
+  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;  // warp grid over the 128x128 CTA tile
+  static constexpr int WM = TILE / WARPS_M_, WN = TILE / WARPS_N_;  // warp tile
+  static constexpr int MI = WM / 8, NI = WN / 8;                // 8x8 mma tiles per warp
+  static constexpr int NTHREADS = 32 * WARPS_M_ * WARPS_N_;
+  static constexpr int NCOPY = KC * TILE / 2 / NTHREADS;        // 16-byte copies per thread per operand per stage
+  static constexpr bool SKIP = SKIP_;
+};
+using CfgBig = GemmCfg<2, 4, false>;
+using CfgSmall = GemmCfg<4, 4, true>;
 constexpr int LD_MC = TILE + 4;  // operand with the tile index contiguous: stage[KC][132]
 constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
 constexpr int STAGE_DOUBLES = TILE * LD_KC;  // 2560 >= KC * LD_MC = 2112
-constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * (int)sizeof(double);  // 163840
+constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 3 * 16 + 8;
+constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * (int)sizeof(double);  // 163840 (the trace epilogue's scratch reuses it)
+static_assert(EPI_SCRATCH_DOUBLES <= STAGES * 2 * STAGE_DOUBLES, "epilogue scratch must fit the pipeline buffers");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -43,8 +59,10 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
-template <bool A_KC, bool B_KC, int EPI>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams p) {
+template <class Cfg, bool A_KC, bool B_KC, int EPI>
+__global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmParams p) {
+  constexpr int WARPS_N = Cfg::WARPS_N, WM = Cfg::WM, WN = Cfg::WN, MI = Cfg::MI, NI = Cfg::NI;
+  constexpr int NTHREADS = Cfg::NTHREADS, NCOPY = Cfg::NCOPY;
   extern __shared__ __align__(16) double smem[];
   const TileTask task = p.tasks[blockIdx.x];
   const long long b = blockIdx.y;
@@ -53,21 +71,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
   const long long lda = p.A.ld, ldb = p.B.ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+  // Warp -> sub-tile map: a Latin square over (warp % WARPS_N, warp / WARPS_N), so that every SM
+  // sub-partition (warp % 4) owns one warp of every row band and one of every column band: when a
+  // triangular operand tile lets some warps skip a chunk, the saved DMMAs are spread evenly over the
+  // four tensor pipes.
+  const int wm = (warp / WARPS_N) * WM, wn = (((warp % WARPS_N) + (warp / WARPS_N)) % WARPS_N) * WN;
 
-  double acc[4][8][2];
+  double acc[NI][MI][2];
 #pragma unroll
-  for (int ni = 0; ni < 4; ni++)
+  for (int ni = 0; ni < NI; ni++)
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++) acc[ni][mi][0] = acc[ni][mi][1] = 0.0;
+    for (int mi = 0; mi < MI; mi++) acc[ni][mi][0] = acc[ni][mi][1] = 0.0;
 
   const int nk = task.k_len / KC;
 
   // per-thread copy descriptors: 4 x 16B for A and 4 x 16B for B per stage
-  const double *srcA[4], *srcB[4];
-  int dstA[4], dstB[4];
+  const double *srcA[NCOPY], *srcB[NCOPY];
+  int dstA[NCOPY], dstB[NCOPY];
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
+  for (int r = 0; r < NCOPY; r++) {
     const int idx = tid + NTHREADS * r;
     if (!A_KC) {
       const int k = idx >> 6, m2 = idx & 63;
@@ -98,16 +120,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
     double *sB = sA + STAGE_DOUBLES;
     const long long offA = (long long)chunk * stepA, offB = (long long)chunk * stepB;
 #pragma unroll
-    for (int r = 0; r < 4; r++) cp_async16(sA + dstA[r], srcA[r] + offA);
+    for (int r = 0; r < NCOPY; r++) cp_async16(sA + dstA[r], srcA[r] + offA);
 #pragma unroll
-    for (int r = 0; r < 4; r++) cp_async16(sB + dstB[r], srcB[r] + offB);
+    for (int r = 0; r < NCOPY; r++) cp_async16(sB + dstB[r], srcB[r] + offB);
   };
-  auto load_frags = [&](const double *sA, const double *sB, int kk, double (&af)[8], double (&bf)[4]) {
+  auto load_frags = [&](const double *sA, const double *sB, int kk, double (&af)[MI], double (&bf)[NI]) {
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
+    for (int mi = 0; mi < MI; mi++)
       af[mi] = A_KC ? sA[(wm + mi * 8 + g) * LD_KC + kk * 4 + t] : sA[(kk * 4 + t) * LD_MC + wm + mi * 8 + g];
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++)
+    for (int ni = 0; ni < NI; ni++)
       bf[ni] = B_KC ? sB[(wn + ni * 8 + g) * LD_KC + kk * 4 + t] : sB[(kk * 4 + t) * LD_MC + wn + ni * 8 + g];
   };
 
@@ -119,12 +141,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
   }
   cp_async_wait<STAGES - 1>();
   __syncthreads();
-  double af[2][8], bf[2][4];
+  double af[2][MI], bf[2][NI];
   load_frags(smem, smem + STAGE_DOUBLES, 0, af[0], bf[0]);
+
+  // Chunks whose products are all zero for this warp because an operand tile is triangular.  A
+  // skipping warp runs only the chunk transition (same barrier count), so the full loop body stays
+  // branch-free and software-pipelined.
+  const int tflags = Cfg::SKIP ? task.flags : 0;
+  auto skip_chunk = [&](int kc) -> bool {
+    if (!(tflags & (TF_A_TRI_FIRST | TF_A_TRI_LAST | TF_B_TRI_FIRST | TF_B_TRI_LAST))) return false;
+    const int kl = kc - (nk - TILE / KC);  // chunk index inside the LAST k-tile (>= 0 there)
+    bool sk = false;
+    if ((tflags & TF_A_TRI_FIRST) && kc < TILE / KC && kc * KC + KC - 1 < wm) sk = true;   // zero where k < m
+    if ((tflags & TF_B_TRI_FIRST) && kc < TILE / KC && kc * KC + KC - 1 < wn) sk = true;   // zero where k < n
+    if ((tflags & TF_A_TRI_LAST) && kl >= 0 && kl * KC > wm + WM - 1) sk = true;           // zero where k > m
+    if ((tflags & TF_B_TRI_LAST) && kl >= 0 && kl * KC > wn + WN - 1) sk = true;           // zero where k > n
+    return sk;
+  };
 
   for (int kc = 0; kc < nk; kc++) {
     const double *sA = smem + (kc % STAGES) * 2 * STAGE_DOUBLES;
     const double *sB = sA + STAGE_DOUBLES;
+    if (skip_chunk(kc)) {  // warp-uniform
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      if (kc + STAGES < nk) load_stage(kc % STAGES, kc + STAGES);
+      cp_async_commit();
+      if (kc + 1 < nk) {
+        const double *nA = smem + ((kc + 1) % STAGES) * 2 * STAGE_DOUBLES;
+        load_frags(nA, nA + STAGE_DOUBLES, 0, af[0], bf[0]);
+      }
+      continue;
+    }
 #pragma unroll
     for (int kk = 0; kk < KC / 4; kk++) {
       const int cur = kk & 1, nxt = cur ^ 1;
@@ -143,9 +191,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
         }
       }
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++)
+      for (int ni = 0; ni < NI; ni++)
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++) dmma884(acc[ni][mi], bf[cur][ni], af[cur][mi]);
+        for (int mi = 0; mi < MI; mi++) dmma884(acc[ni][mi], bf[cur][ni], af[cur][mi]);
     }
   }
   cp_async_wait<0>();
@@ -155,10 +203,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
     const double *__restrict__ C0 = p.C0.p ? p.C0.p + b * p.C0.stride : nullptr;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++) {
+    for (int ni = 0; ni < NI; ni++) {
       const int n = task.c_c + wn + ni * 8 + g;
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++) {
+      for (int mi = 0; mi < MI; mi++) {
         const int m = task.c_r + wm + mi * 8 + 2 * t;
         double2 v = make_double2(alpha * acc[ni][mi][0], alpha * acc[ni][mi][1]);
         if (C0) {
@@ -180,7 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
       const int i = task.c_r + tid;
       xr[tid] = (i < p.n) ? x[i] : 0.0;
       ar[tid] = (i < p.n) ? av[i] : 0.0;
-    } else {
+    } else if (tid < 2 * TILE) {
       const int j = task.c_c + tid - TILE;
       xc[tid - TILE] = (j < p.n) ? x[j] : 0.0;
       ac[tid - TILE] = (j < p.n) ? av[j] : 0.0;
@@ -192,11 +240,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
     double s_se = 0.0, s_d2 = 0.0, s_tr = 0.0;
     double *__restrict__ C = p.C.p ? p.C.p + b * p.C.stride : nullptr;
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++) {
+    for (int ni = 0; ni < NI; ni++) {
       const int nl = wn + ni * 8 + g;
       const int j = task.c_c + nl;
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++) {
+      for (int mi = 0; mi < MI; mi++) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int ml = wm + mi * 8 + 2 * t + e;
@@ -250,39 +298,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tile_kernel(const GemmParams
   }
 }
 
-template <bool A_KC, bool B_KC, int EPI>
+template <class Cfg, bool A_KC, bool B_KC, int EPI>
 static int launch_one(Handle *h, const GemmParams &p, int ntasks, int batch) {
-  auto kern = gemm_tile_kernel<A_KC, B_KC, EPI>;
+  auto kern = gemm_tile_kernel<Cfg, A_KC, B_KC, EPI>;
   dim3 grid(ntasks, batch);
   ProfScope ps__(h, PC_GEMM);
-  kern<<<grid, NTHREADS, GEMM_SMEM_BYTES, h->stream>>>(p);
+  kern<<<grid, Cfg::NTHREADS, GEMM_SMEM_BYTES, h->stream>>>(p);
   GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+template <class Cfg>
+static int smem_setup_cfg(Handle *h) {
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   return 0;
 }
 
 // The opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: it is set when a
 // handle is created (gpb200_create), once per handle, so one process may hold handles on several GPUs.
 int gemm_smem_setup(Handle *h) {
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<false, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  return 0;
+  int rc = smem_setup_cfg<CfgBig>(h);
+  return rc ? rc : smem_setup_cfg<CfgSmall>(h);
 }
 
-int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
-  if (ntasks <= 0 || batch <= 0) return 0;
+template <class Cfg>
+static int launch_cfg(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
   if (epi == EPI_AXPBY) {
     switch (layout) {
-      case LAYOUT_NT: return launch_one<false, false, EPI_AXPBY>(h, p, ntasks, batch);
-      case LAYOUT_TN: return launch_one<true, true, EPI_AXPBY>(h, p, ntasks, batch);
-      case LAYOUT_NN: return launch_one<false, true, EPI_AXPBY>(h, p, ntasks, batch);
+      case LAYOUT_NT: return launch_one<Cfg, false, false, EPI_AXPBY>(h, p, ntasks, batch);
+      case LAYOUT_TN: return launch_one<Cfg, true, true, EPI_AXPBY>(h, p, ntasks, batch);
+      case LAYOUT_NN: return launch_one<Cfg, false, true, EPI_AXPBY>(h, p, ntasks, batch);
     }
-  } else {
-    if (layout == LAYOUT_TN) return launch_one<true, true, EPI_TRACE>(h, p, ntasks, batch);
+  } else if (layout == LAYOUT_TN) {
+    return launch_one<Cfg, true, true, EPI_TRACE>(h, p, ntasks, batch);
   }
   snprintf(h->err, sizeof(h->err), "launch_gemm: unsupported layout/epilogue %d/%d", (int)layout, (int)epi);
   return -2;
+}
+
+// `small` selects the 16-warp zero-skipping configuration (short k-loops)
+int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
+  if (ntasks <= 0 || batch <= 0) return 0;
+  const bool small = h->gemm_cfg_override ? h->gemm_cfg_override == 2 : p.small_k;
+  return small ? launch_cfg<CfgSmall>(h, layout, epi, p, ntasks, batch) : launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
 }
 
 }  // namespace gpb

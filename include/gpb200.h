@@ -56,6 +56,10 @@ GPB200_API long long gpb200_graph_replays(gpb200_handle_t h);
  * for batches >= 64, 8-tile panels + right-looking trailing updates for small batches) */
 GPB200_API int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles);
 
+/* tuning/testing knob: GEMM configuration (0 = automatic: 16 warps of 32x32 with triangular
+ * zero-skipping for matrices of up to 12 tiles per dimension, 8 warps of 64x32 beyond; 1 / 2 force one) */
+GPB200_API int gpb200_set_gemm_config(gpb200_handle_t h, int cfg);
+
 /* per-kernel-class timing with CUDA events on the handle's stream (used by bench.py for the
  * roofline of the dominant kernel).  Classes: 0 DMMA tile GEMM, 1 POTRF tile, 2 TRSM tile,
  * 3 Gram, 4 triangular mat-vec/solves, 5 other.  get_profile synchronises, sums and resets. */
