@@ -251,6 +251,28 @@ def main():
     assert int(dinfo.abs().sum().item()) == 0, "a synthetic draw was not positive definite"
     lml_dev = dlml.cpu().numpy().copy()
 
+    # ---------------- second half of BASELINE's metric: Cholesky FP64 TFLOP/s vs peak ------------
+    # the LML-only pass (Gram -> tiled Cholesky -> forward substitution -> log-det/quadratic form) of
+    # the same batch, N^3/3 flops per evaluation (LAPACK convention), timed apart from the headline
+    def step_chol():
+        h.lml_grad_batched_device(N, B, dx, 0, dy, 0, dth, 0.0, False, dlml, dgrad, dinfo)
+
+    step_chol()
+    barrier()
+    c0 = torch.cuda.Event(enable_timing=True)
+    c1 = torch.cuda.Event(enable_timing=True)
+    kc = max(1, min(K, 3))
+    c0.record(stream)
+    for _ in range(kc):
+        step_chol()
+    c1.record(stream)
+    barrier()
+    t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    chol_ms = float(t.item()) / kc
+    chol_tflops = B * float(N) ** 3 / 3.0 / (chol_ms * 1e-3) * 1e-12   # per GPU
+
     # ---------------- e2e: host (pinned) buffers through the C ABI ----------------------------
     h.set_pointer_mode(False)
     hx = torch.from_numpy(x).pin_memory()
@@ -316,6 +338,10 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline}
+    peak_c, _ = fp64_peak()
+    line["cholesky"] = {"tflops_per_gpu": chol_tflops, "peak": peak_c, "frac": chol_tflops / peak_c, "ms_per_step": chol_ms,
+                        "what": "LML-only pass of the same batch (Gram + left-looking tiled Cholesky + forward "
+                                "substitution), N^3/3 flops per evaluation, CUDA events, max over ranks"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

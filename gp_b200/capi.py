@@ -57,6 +57,8 @@ SIGNATURES = {
     "gpb200_lml_grad": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "gpb200_lml_grad_batched": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, _ll, C.c_void_p,
                                           C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpb200_lml_grad_deriv_batched": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, _ll,
+                                                C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpb200_rbf_cov_chol": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "gpb200_rbf_cov_chol_batched": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p]),
@@ -70,6 +72,9 @@ SIGNATURES = {
                                       C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "gpb200_cond_mvn": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int]),
+    "gpb200_normal_fill": (C.c_int, [_h, C.c_ulonglong, C.c_ulonglong, _ll, C.c_void_p]),
+    "gpb200_mvrnorm": (C.c_int, [_h, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_ulonglong,
+                                 C.c_void_p, C.c_int]),
     "gpb200_mg_gram_panel": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, _ll]),
     "gpb200_mg_panel_factor": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p]),
@@ -328,6 +333,28 @@ class Handle:
                                                      jitter, int(want_grad), _ptr(lml), _ptr(grad), _ptr(info)),
                     "lml_grad_batched")
 
+    def lml_grad_deriv_batched(self, t, y, theta, jitter=0.0, order0=0, nblocks=None, want_grad=True):
+        """GP observed through derivative orders order0 .. order0+nblocks-1 on the grid t.
+        t: (n,) shared or (B, n); y: (n*nblocks,) or (B, n*nblocks), blocks stacked by order;
+        theta: (B, 2+nblocks) = (alpha, rho, noise[nblocks]).  Returns lml[B], grad[B, 2+nblocks], info[B]."""
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        B = th.shape[0]
+        if nblocks is None:
+            nblocks = th.shape[1] - 2
+        if th.ndim != 2 or th.shape[1] != 2 + nblocks:
+            raise ValueError("theta must be (B, 2 + nblocks)")
+        t = np.ascontiguousarray(t, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+        n = t.shape[-1]
+        if y.shape[-1] != n * nblocks:
+            raise ValueError("y must hold n * nblocks stacked observations")
+        t_s = n if t.ndim == 2 else 0
+        y_s = n * nblocks if y.ndim == 2 else 0
+        lml = np.empty(B); grad = np.empty((B, 2 + nblocks)); info = np.zeros(B, dtype=np.int32)
+        self._check(self.lib.gpb200_lml_grad_deriv_batched(self._h, n, order0, nblocks, B, _ptr(t), t_s, _ptr(y), y_s,
+                                                           _ptr(th), jitter, int(want_grad), _ptr(lml), _ptr(grad),
+                                                           _ptr(info)), "lml_grad_deriv_batched")
+        return lml, grad, info
+
     # -- a1-a3 / f-1 ----------------------------------------------------------------------------
     def rbf_cov_chol(self, x1, l):
         x1 = np.ascontiguousarray(x1, dtype=np.float64).ravel()
@@ -402,6 +429,22 @@ class Handle:
         self._check(self.lib.gpb200_cond_mvn(self._h, ng, nd, _ptr(mean_a), _ptr(sigma), N, _ptr(xg), _ptr(cm),
                                              _ptr(cv), nd), "cond_mvn")
         return cm, cv
+
+    # -- f-4 ---------------------------------------------------------------------------------------
+    def normal_fill(self, seed, n, offset=0):
+        out = np.empty(int(n))
+        self._check(self.lib.gpb200_normal_fill(self._h, int(seed), int(offset), int(n), _ptr(out)), "normal_fill")
+        return out
+
+    def mvrnorm(self, ndraws, mu, Sigma, seed, jitter=0.0):
+        """MASS::mvrnorm(ndraws, mu, Sigma): (ndraws, m) array (a vector when ndraws == 1, like R)."""
+        S = _f(Sigma)
+        m = S.shape[0]
+        mu_a = None if mu is None else np.ascontiguousarray(mu, dtype=np.float64)
+        out = np.empty((ndraws, m), order="F")
+        self._check(self.lib.gpb200_mvrnorm(self._h, int(ndraws), m, _ptr(mu_a), _ptr(S), max(m, 1), float(jitter),
+                                            int(seed), _ptr(out), max(ndraws, 1)), "mvrnorm")
+        return out[0].copy() if ndraws == 1 else np.ascontiguousarray(out)
 
 
 _default = {}

@@ -8,14 +8,17 @@ using namespace gpb;
 // =================================================================================================
 // CS-A fused LML + gradient
 // =================================================================================================
-extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const double *x, long long x_stride,
-                                       const double *y, long long y_stride, const double *theta, double jitter,
-                                       int want_grad, double *lml, double *grad, int *info) {
-  CHECK_H(h);
-  if (n < 1) BAD_ARG(h, 2, "lml_grad_batched: n must be >= 1");
-  if (B < 0) BAD_ARG(h, 3, "lml_grad_batched: negative batch");
-  if (x_stride != 0 && x_stride < n) BAD_ARG(h, 5, "lml_grad_batched: x_stride < n");
-  if (y_stride != 0 && y_stride < n) BAD_ARG(h, 7, "lml_grad_batched: y_stride < n");
+namespace {
+// which covariance the fused path assembles: the SE kernel of fit_hyperparameters.stan (deriv = false,
+// theta = (alpha, rho, sigma)) or the joint derivative-observation covariance (deriv = true,
+// theta = (alpha, rho, noise[nblocks])) on a grid of n_grid points
+struct LmlSpec { bool deriv; int n_grid, order0, nblocks; };
+
+int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long long x_stride,
+             const double *y, long long y_stride, const double *theta, double jitter,
+             int want_grad, double *lml, double *grad, int *info) {
+  const int ng = sp.n_grid, n = sp.n_grid * sp.nblocks, ts = sp.deriv ? 2 + sp.nblocks : 3;
+  const int pw = sp.deriv ? 8 : 4;  // doubles per tile partial
   if (B == 0) return 0;
   const int np = round_up(n, TILE), nt = np / TILE;
   const long long mat = (long long)np * np;
@@ -25,9 +28,9 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
 
   // chunk the batch so that the resident set fits the workspace limit.  cudaMemGetInfo costs
   // milliseconds with tens of GB allocated, so it is only consulted when the workspace must grow.
-  const size_t per_item = pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)ntasks * 32) + 64;
-  const size_t fixed = pad256((size_t)B * (x_stride ? n : 0) * 8 + n * 8) + pad256((size_t)B * (y_stride ? n : 0) * 8 + n * 8) +
-                       pad256((size_t)B * 24) + pad256((size_t)B * 8) + pad256((size_t)B * 24) + pad256((size_t)B * 4) + 4096;
+  const size_t per_item = pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)ntasks * pw * 8) + 64;
+  const size_t fixed = pad256((size_t)B * (x_stride ? ng : 0) * 8 + ng * 8) + pad256((size_t)B * (y_stride ? n : 0) * 8 + n * 8) +
+                       2 * pad256((size_t)B * ts * 8) + pad256((size_t)B * 8) + pad256((size_t)B * 4) + 4096;
   int Bc = B;
   if (h->ws_limit > 0 || fixed + per_item * (size_t)B + 8192 > h->ws_bytes) {
     size_t limit = (size_t)h->ws_limit;
@@ -43,15 +46,15 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
   Arena a;
   RC(ws_reserve(h, fixed + per_item * (size_t)Bc + 8192, &a));
 
-  const long long xs = x_stride ? n : 0, ys = y_stride ? n : 0;
-  double *dx = a.take<double>(x_stride ? (size_t)B * n : n);
+  const long long xs = x_stride ? ng : 0, ys = y_stride ? n : 0;
+  double *dx = a.take<double>(x_stride ? (size_t)B * ng : ng);
   double *dy = a.take<double>(y_stride ? (size_t)B * n : n);
-  double *dth = a.take<double>((size_t)B * 3);
-  double *dlml = a.take<double>(B), *dgrad = a.take<double>((size_t)B * 3);
+  double *dth = a.take<double>((size_t)B * ts);
+  double *dlml = a.take<double>(B), *dgrad = a.take<double>((size_t)B * ts);
   int *dinfo = a.take<int>(B);
   double *Lbuf = a.take<double>((size_t)Bc * mat), *Sbuf = a.take<double>((size_t)Bc * mat);
   double *zbuf = a.take<double>((size_t)Bc * np), *abuf = a.take<double>((size_t)Bc * np), *dvec = a.take<double>((size_t)Bc * np);
-  double *partial = a.take<double>((size_t)Bc * ntasks * 4);
+  double *partial = a.take<double>((size_t)Bc * ntasks * pw);
   if (!partial) BAD_ARG(h, 1002, "lml_grad_batched: workspace arithmetic error");
 
   // The kernel sequence (everything between staging the inputs and reading the outputs).
@@ -59,8 +62,9 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
     GPB_CUDA(h, cudaMemsetAsync(dinfo, 0, (size_t)B * sizeof(int), h->stream));
     for (int b0 = 0; b0 < B; b0 += Bc) {
       const int bc = std::min(Bc, B - b0);
-      const double *cx = dx + (long long)b0 * xs, *cy = dy + (long long)b0 * ys, *cth = dth + (long long)b0 * 3;
-      RC(launch_gram_se_batched(h, n, np, cx, xs, cth, jitter, 1, Lbuf, mat, bc));
+      const double *cx = dx + (long long)b0 * xs, *cy = dy + (long long)b0 * ys, *cth = dth + (long long)b0 * ts;
+      if (sp.deriv) RC(launch_gram_deriv_batched(h, ng, sp.order0, sp.nblocks, np, cx, xs, cth, ts, jitter, 1, Lbuf, mat, bc));
+      else RC(launch_gram_se_batched(h, n, np, cx, xs, cth, jitter, 1, Lbuf, mat, bc));
       RC(chol_batched(h, Lbuf, np, mat, n, bc, dinfo + b0, nullptr));
       RC(extract_diag(h, np, Lbuf, mat, dvec, bc));
       if (want_grad) {
@@ -79,13 +83,18 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
         p.partial = partial;
         p.n = n;
         p.ntasks = ntasks;
-        RC(launch_gemm(h, LAYOUT_TN, EPI_TRACE, p, ntasks, bc));
+        p.n_grid = ng; p.order0 = sp.order0; p.theta_stride = ts;
+        RC(launch_gemm(h, LAYOUT_TN, sp.deriv ? EPI_TRACE_DERIV : EPI_TRACE, p, ntasks, bc));
       } else {
         RC(launch_tile_inverse(h, Lbuf, Sbuf, np, mat, nt, bc));
         if (bc >= 32) RC(launch_trsv_blocked(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, np, bc));
         else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
       }
-      RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
+      if (sp.deriv)
+        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0,
+                                 dgrad + (long long)b0 * ts, bc));
+      else
+        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
     }
     return 0;
   };
@@ -101,17 +110,18 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
   }
   int rc = 0;
   do {
-    if (x_stride) rc = to_device_2d(h, x, x_stride, dx, n, n, B); else rc = to_device(h, x, dx, n);
+    if (x_stride) rc = to_device_2d(h, x, x_stride, dx, ng, ng, B); else rc = to_device(h, x, dx, ng);
     if (rc) break;
     if (y_stride) rc = to_device_2d(h, y, y_stride, dy, n, n, B); else rc = to_device(h, y, dy, n);
     if (rc) break;
-    if ((rc = to_device(h, theta, dth, (size_t)B * 3))) break;
+    if ((rc = to_device(h, theta, dth, (size_t)B * ts))) break;
     if (!use_graph) {
       rc = run_sequence();
     } else {
       long long jbits;
       memcpy(&jbits, &jitter, sizeof(jbits));
-      const std::vector<long long> key = {n, B, want_grad, xs, ys, jbits, (long long)(uintptr_t)h->ws, h->chol_panel_override};
+      const std::vector<long long> key = {n, B, want_grad, xs, ys, jbits, (long long)(uintptr_t)h->ws, h->chol_panel_override,
+                                          sp.deriv, sp.order0, sp.nblocks};
       auto it = h->graphs.find(key);
       if (it == h->graphs.end()) {
         // task lists allocate and synchronise on first use: make sure they exist before the capture
@@ -137,7 +147,7 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
     }
     if (rc) break;
     if ((rc = from_device(h, dlml, lml, (size_t)B * sizeof(double)))) break;
-    if (want_grad && grad && (rc = from_device(h, dgrad, grad, (size_t)B * 3 * sizeof(double)))) break;
+    if (want_grad && grad && (rc = from_device(h, dgrad, grad, (size_t)B * ts * sizeof(double)))) break;
     if (info && (rc = from_device(h, dinfo, info, (size_t)B * sizeof(int)))) break;
     rc = finish(h);
   } while (0);
@@ -146,8 +156,35 @@ extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
     cudaEventRecord(h->g_out, h->gstream);
     cudaStreamWaitEvent(user_stream, h->g_out, 0);
   }
-  if (rc && !h->err[0]) snprintf(h->err, sizeof(h->err), "lml_grad_batched: CUDA graph path failed (%d)", rc);
+  if (rc && !h->err[0]) snprintf(h->err, sizeof(h->err), "lml_grad: CUDA graph path failed (%d)", rc);
   return rc;
+}
+}  // namespace
+
+extern "C" int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const double *x, long long x_stride,
+                                       const double *y, long long y_stride, const double *theta, double jitter,
+                                       int want_grad, double *lml, double *grad, int *info) {
+  CHECK_H(h);
+  if (n < 1) BAD_ARG(h, 2, "lml_grad_batched: n must be >= 1");
+  if (B < 0) BAD_ARG(h, 3, "lml_grad_batched: negative batch");
+  if (x_stride != 0 && x_stride < n) BAD_ARG(h, 5, "lml_grad_batched: x_stride < n");
+  if (y_stride != 0 && y_stride < n) BAD_ARG(h, 7, "lml_grad_batched: y_stride < n");
+  return lml_core(h, LmlSpec{false, n, 0, 1}, B, x, x_stride, y, y_stride, theta, jitter, want_grad, lml, grad, info);
+}
+
+extern "C" int gpb200_lml_grad_deriv_batched(gpb200_handle_t h, int n, int order0, int nblocks, int B, const double *t,
+                                             long long t_stride, const double *y, long long y_stride,
+                                             const double *theta, double jitter, int want_grad, double *lml,
+                                             double *grad, int *info) {
+  CHECK_H(h);
+  if (n < 1) BAD_ARG(h, 2, "lml_grad_deriv_batched: n must be >= 1");
+  if (order0 < 0 || nblocks < 1 || order0 + nblocks > 3)
+    BAD_ARG(h, 3, "lml_grad_deriv_batched: derivative orders must lie in 0..2 (order0 >= 0, nblocks >= 1, order0 + nblocks <= 3)");
+  if (B < 0) BAD_ARG(h, 5, "lml_grad_deriv_batched: negative batch");
+  if ((long long)n * nblocks > 2147483647LL / 2) BAD_ARG(h, 2, "lml_grad_deriv_batched: n * nblocks too large");
+  if (t_stride != 0 && t_stride < n) BAD_ARG(h, 7, "lml_grad_deriv_batched: t_stride < n");
+  if (y_stride != 0 && y_stride < (long long)n * nblocks) BAD_ARG(h, 9, "lml_grad_deriv_batched: y_stride < n * nblocks");
+  return lml_core(h, LmlSpec{true, n, order0, nblocks}, B, t, t_stride, y, y_stride, theta, jitter, want_grad, lml, grad, info);
 }
 
 // number of CUDA-graph replays so far (small evaluations are replayed as one graph)

@@ -49,6 +49,9 @@ struct GemmParams {
   double *partial;                           // B x ntasks x 4
   int n;                                     // true matrix size (mask for the padding)
   int ntasks;
+  // derivative-observation trace epilogue (EPI_TRACE_DERIV): the matrix is nblocks x nblocks blocks of
+  // n_grid x n_grid; block b carries derivative order order0 + b; theta is B x theta_stride
+  int n_grid, order0, theta_stride;
   int small_k;                               // 1: short k-loops -> 16-warp zero-skipping GEMM configuration
 };
 
@@ -136,7 +139,7 @@ struct ProfScope {
 
 // ---- launchers implemented in the .cu files --------------------------------------------------
 enum GemmLayout { LAYOUT_NT = 0, LAYOUT_TN = 1, LAYOUT_NN = 2 };
-enum GemmEpi { EPI_AXPBY = 0, EPI_TRACE = 1 };
+enum GemmEpi { EPI_AXPBY = 0, EPI_TRACE = 1, EPI_TRACE_DERIV = 2 };
 
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch);
 int gemm_smem_setup(Handle *h);

@@ -41,7 +41,7 @@ using CfgSmall = GemmCfg<4, 4, true>;
 constexpr int LD_MC = TILE + 4;  // operand with the tile index contiguous: stage[KC][132]
 constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
 constexpr int STAGE_DOUBLES = TILE * LD_KC;  // 2560 >= KC * LD_MC = 2112
-constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 3 * 16 + 8;
+constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 5 * 16 + 8;
 constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * (int)sizeof(double);  // 163840 (the trace epilogue's scratch reuses it)
 static_assert(EPI_SCRATCH_DOUBLES <= STAGES * 2 * STAGE_DOUBLES, "epilogue scratch must fit the pipeline buffers");
 
@@ -217,6 +217,94 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
         *reinterpret_cast<double2 *>(C + m + (long long)n * p.C.ld) = v;
       }
     }
+  } else if (EPI == EPI_TRACE_DERIV) {
+    // ---- fused trace epilogue for the joint derivative-observation covariance -------------------
+    // K[I,J] = alpha^2 k_pq(t_i - t_j) (+ diagonal), p / q the derivative orders of row / column block:
+    //   k_pq(d)      = (-1)^p He_m(u) l^-m e,  m = p + q, u = d / l, e = exp(-u^2 / 2)
+    //   d k_pq / d l = (-1)^p l^-(m+1) e (He_{m+2}(u) + He_m(u))
+    // (He = probabilists' Hermite polynomials; restates derivative_kernels.R:39-73 -- checked against
+    // those nine closed forms in tests/).  Partials per tile: sum M k, sum M dk/dl, tr G per block.
+    __syncthreads();
+    double *xr = smem, *xc = smem + TILE, *ar = smem + 2 * TILE, *ac = smem + 3 * TILE;
+    double *red = smem + 4 * TILE;
+    const int ng = p.n_grid;
+    const double *x = p.x + b * p.x_stride;
+    const double *av = p.avec + b * p.a_stride;
+    if (tid < TILE) {
+      const int i = task.c_r + tid;
+      const int gi = i - (i >= ng ? ng : 0) - (i >= 2 * ng ? ng : 0);
+      xr[tid] = (i < p.n) ? x[gi] : 0.0;
+      ar[tid] = (i < p.n) ? av[i] : 0.0;
+    } else if (tid < 2 * TILE) {
+      const int j = task.c_c + tid - TILE;
+      const int gj = j - (j >= ng ? ng : 0) - (j >= 2 * ng ? ng : 0);
+      xc[tid - TILE] = (j < p.n) ? x[gj] : 0.0;
+      ac[tid - TILE] = (j < p.n) ? av[j] : 0.0;
+    }
+    __syncthreads();
+    const double l = p.theta[b * p.theta_stride + 1];
+    const double il = 1.0 / l;
+    const bool diag_tile = (task.flags & 1) != 0;
+    double s_k = 0.0, s_dk = 0.0, s_tr[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++) {
+      const int nl = wn + ni * 8 + g;
+      const int j = task.c_c + nl;
+      const int bj = (j >= ng) + (j >= 2 * ng);
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int ml = wm + mi * 8 + 2 * t + e;
+          const int i = task.c_r + ml;
+          const double G = acc[ni][mi][e];
+          if (i < p.n && j < p.n) {
+            const int bi = (i >= ng) + (i >= 2 * ng);
+            const int pi = p.order0 + bi, m = pi + p.order0 + bj;
+            const double u = (xr[ml] - xc[nl]) * il;
+            const double ek = exp(-0.5 * u * u);
+            double hp = 0.0, hc = 1.0, lp = 1.0, hm = 1.0, lm = 1.0, hm2 = 0.0;
+#pragma unroll
+            for (int k = 1; k <= 6; k++) {
+              const double hn = u * hc - (double)(k - 1) * hp;
+              hp = hc; hc = hn; lp *= il;
+              if (k == m) { hm = hc; lm = lp; }
+              if (k == m + 2) hm2 = hc;
+            }
+            const double sg = (pi & 1) ? -ek : ek;
+            const double M = ar[ml] * ac[nl] - G;
+            s_k += M * (sg * hm * lm);
+            s_dk += M * (sg * lm * il * (hm2 + hm));
+            if (diag_tile && i == j) {
+              if (bi == 0) s_tr[0] += G; else if (bi == 1) s_tr[1] += G; else s_tr[2] += G;
+            }
+          }
+        }
+      }
+    }
+    const double w = diag_tile ? 1.0 : 2.0;
+    s_k *= w;
+    s_dk *= w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_k += __shfl_xor_sync(0xffffffffu, s_k, o);
+      s_dk += __shfl_xor_sync(0xffffffffu, s_dk, o);
+#pragma unroll
+      for (int q = 0; q < 3; q++) s_tr[q] += __shfl_xor_sync(0xffffffffu, s_tr[q], o);
+    }
+    if (lane == 0) {
+      red[warp * 5 + 0] = s_k;
+      red[warp * 5 + 1] = s_dk;
+      red[warp * 5 + 2] = s_tr[0];
+      red[warp * 5 + 3] = s_tr[1];
+      red[warp * 5 + 4] = s_tr[2];
+    }
+    __syncthreads();
+    if (tid < 5) {
+      double r = 0.0;
+      for (int w8 = 0; w8 < NTHREADS / 32; w8++) r += red[w8 * 5 + tid];
+      p.partial[((long long)b * p.ntasks + blockIdx.x) * 8 + tid] = r;
+    }
   } else {
     // ---- fused trace epilogue: this tile of G = K^-1 never has to reach HBM -----------------
     __syncthreads();  // everyone is done with the pipeline buffers
@@ -314,6 +402,7 @@ static int smem_setup_cfg(Handle *h) {
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE_DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   return 0;
 }
 
@@ -333,6 +422,7 @@ static int launch_cfg(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParam
       case LAYOUT_NN: return launch_one<Cfg, false, true, EPI_AXPBY>(h, p, ntasks, batch);
     }
   } else if (layout == LAYOUT_TN) {
+    if (epi == EPI_TRACE_DERIV) return launch_one<Cfg, true, true, EPI_TRACE_DERIV>(h, p, ntasks, batch);
     return launch_one<Cfg, true, true, EPI_TRACE>(h, p, ntasks, batch);
   }
   snprintf(h->err, sizeof(h->err), "launch_gemm: unsupported layout/epilogue %d/%d", (int)layout, (int)epi);

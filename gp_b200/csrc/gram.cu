@@ -214,6 +214,56 @@ __global__ void __launch_bounds__(256) gram_deriv_kernel(int n, int nblocks, con
   }
 }
 
+// Batched padded form of the same matrix for the fused LML path: derivative orders order0 .. order0 +
+// nblocks - 1 of one grid t (n points) per item; theta = (alpha, rho, noise[nblocks]) per item; identity
+// in the padding; only tiles with tile_row >= tile_col when lower_only.  Element values come from the
+// same kern_value as gram_deriv_kernel, so both produce identical bits.
+__global__ void __launch_bounds__(256) gram_deriv_batched_kernel(int n, int order0, int nblocks, int np,
+                                                                const double *__restrict__ t, long long t_stride,
+                                                                const double *__restrict__ theta, int theta_stride,
+                                                                double jitter, int lower_only,
+                                                                double *__restrict__ K, long long stride) {
+  const int nt = np / TILE;
+  const int tr = blockIdx.x % nt, tc = blockIdx.x / nt;
+  if (lower_only && tr < tc) return;
+  __shared__ double xs[TILE], ys[TILE];
+  __shared__ int bxs[TILE], bys[TILE];
+  const long long b = blockIdx.y;
+  const double *tb = t + b * t_stride;
+  const int N = n * nblocks;
+  const int r0 = tr * TILE, c0 = tc * TILE, tid = threadIdx.x;
+  {
+    const int I = (tid < TILE) ? r0 + tid : c0 + tid - TILE;
+    const int blk = (I < N) ? I / n : 0;
+    const double v = (I < N) ? tb[I - blk * n] : 0.0;
+    if (tid < TILE) { xs[tid] = v; bxs[tid] = blk; }
+    else { ys[tid - TILE] = v; bys[tid - TILE] = blk; }
+  }
+  __syncthreads();
+  const double *th = theta + b * theta_stride;
+  const double alpha = th[0], rho = th[1];
+  const double amp2 = alpha * alpha;
+  double *Kb = K + b * stride;
+  const int rl = 2 * (tid & 63), cq = tid >> 6;
+  for (int s = 0; s < 32; s++) {
+    const int cl = cq + 4 * s;
+    const int J = c0 + cl;
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int I = r0 + rl + e;
+      if (I < N && J < N) {
+        const int bi = bxs[rl + e], bj = bys[cl];
+        v[e] = kern_value(c_joint_kind[order0 + bi][order0 + bj], xs[rl + e], ys[cl], rho, amp2);
+        if (I == J) { const double nz = th[2 + bi]; v[e] += nz * nz + jitter; }
+      } else {
+        v[e] = (I == J) ? 1.0 : 0.0;
+      }
+    }
+    *reinterpret_cast<double2 *>(Kb + (r0 + rl) + (long long)J * np) = make_double2(v[0], v[1]);
+  }
+}
+
 // ---- QQard (R/kernels.R:19) ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gram_ard_kernel(int n, int m, int D, const double *__restrict__ X, long long ldx,
                                                       const double *__restrict__ Y, long long ldy, double alpha,
@@ -331,6 +381,18 @@ int launch_gram_deriv(Handle *h, int n, int nblocks, const double *t, double alp
   ProfScope ps__(h, PC_GRAM);
   gram_deriv_kernel<<<grid, 256, 0, h->stream>>>(n, nblocks, t, alpha, rho, noise[0], nblocks > 1 ? noise[1] : 0.0,
                                                 nblocks > 2 ? noise[2] : 0.0, jitter, quirk, K, ldk);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_gram_deriv_batched(Handle *h, int n, int order0, int nblocks, int np, const double *t, long long t_stride,
+                              const double *theta, int theta_stride, double jitter, int lower_only, double *K,
+                              long long stride, int batch) {
+  const int nt = np / TILE;
+  dim3 grid(nt * nt, batch);
+  ProfScope ps__(h, PC_GRAM);
+  gram_deriv_batched_kernel<<<grid, 256, 0, h->stream>>>(n, order0, nblocks, np, t, t_stride, theta, theta_stride, jitter,
+                                                        lower_only, K, stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

@@ -16,6 +16,9 @@ int launch_gram_tangent(Handle *h, int n, int np, const double *x, double alpha,
                         double *S, double *Sdot, long long stride, int batch);
 int launch_gram_deriv(Handle *h, int n, int nblocks, const double *t, double alpha, double rho, const double *noise,
                       double jitter, int quirk, double *K, long long ldk);
+int launch_gram_deriv_batched(Handle *h, int n, int order0, int nblocks, int np, const double *t, long long t_stride,
+                              const double *theta, int theta_stride, double jitter, int lower_only, double *K,
+                              long long stride, int batch);
 int launch_gram_ard(Handle *h, int n, int m, int D, const double *X, long long ldx, const double *Y, long long ldy,
                     double alpha, const double *rho, int rho_len, double *K, long long ldk);
 
@@ -41,6 +44,9 @@ int launch_trsv_sweep(Handle *h, int np, const double *L, const double *Wdiag, l
                       int batch);
 int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec, const double *z, const double *a,
                     const double *partial, int ntasks, const double *theta, double *lml, double *grad, int batch);
+int launch_finalize_deriv(Handle *h, int n_grid, int nblocks, int np, int want_grad, const double *dvec, const double *z,
+                          const double *a, const double *partial, int ntasks, const double *theta, double *lml,
+                          double *grad, int batch);
 int launch_pack(Handle *h, int rows, int cols, const double *src, long long lds, int rp, int cp, double *dst,
                 int mode, double diag_add);
 int launch_unpack(Handle *h, int rows, int cols, const double *src, long long lds_src, double *dst, long long ldd,
@@ -51,5 +57,11 @@ int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv,
 int launch_hermite(Handle *h, long long len, int n, const double *y1, const double *y2, const double *k1,
                    const double *k2, double x1, double x2, double l, double *v, double *dvdl);
 int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2);
+
+// rng.cu
+int launch_normal_fill(Handle *h, unsigned long long seed, unsigned long long offset, long long len, int rows,
+                       long long ld, double *out);
+int launch_add_mean_transpose(Handle *h, int m, int ndraws, const double *X, long long ldx, const double *mu,
+                              double *out, long long ldo);
 
 }  // namespace gpb

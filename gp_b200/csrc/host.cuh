@@ -34,7 +34,7 @@ int ws_reserve(Handle *h, size_t bytes, Arena *a);
 
 // ---- tile task lists (host-built once per tile count, cached on the device) ---------------------
 enum TaskKind { TK_CHOL = 1, TK_CHOL_TRAIL, TK_TRTRI_S, TK_TRTRI_W, TK_LAUUM, TK_TAN_T1, TK_TAN_A, TK_TAN_LDOT, TK_COND_V,
-                TK_COND_COV, TK_MUL_WB, TK_MUL_WTB };
+                TK_COND_COV, TK_MUL_WB, TK_MUL_WTB, TK_MUL_LZ };
 
 struct TaskList {
   const TileTask *dev = nullptr;

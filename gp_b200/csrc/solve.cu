@@ -400,6 +400,66 @@ int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec,
   return 0;
 }
 
+// The same for the derivative-observation LML (EPI_TRACE_DERIV partials: 8 doubles per tile = sum M k,
+// sum M dk/dl, tr G over each of up to three blocks); theta = (alpha, rho, noise[nblocks]) per item,
+// grad in the same layout.
+__global__ void __launch_bounds__(256) finalize_deriv_kernel(int n_grid, int nblocks, int np, int want_grad,
+                                                            const double *__restrict__ dvec, const double *__restrict__ z,
+                                                            const double *__restrict__ a,
+                                                            const double *__restrict__ partial, int ntasks,
+                                                            const double *__restrict__ theta, double *__restrict__ lml,
+                                                            double *__restrict__ grad) {
+  __shared__ double red[8][10];
+  const long long b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = n_grid * nblocks, ts = 2 + nblocks;
+  double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // logdet, quad, aa[3], sum_k, sum_dk, tr[3]
+  for (int i = tid; i < n; i += 256) {
+    v[0] += log(dvec[b * np + i]);
+    const double zi = z[b * np + i];
+    v[1] = fma(zi, zi, v[1]);
+    if (want_grad) {
+      const double ai = a[b * np + i];
+      const int blk = (i >= n_grid) + (i >= 2 * n_grid);
+      if (blk == 0) v[2] = fma(ai, ai, v[2]); else if (blk == 1) v[3] = fma(ai, ai, v[3]); else v[4] = fma(ai, ai, v[4]);
+    }
+  }
+  if (want_grad)
+    for (int q = tid; q < ntasks; q += 256) {
+      const double *pp = partial + (b * ntasks + q) * 8;
+#pragma unroll
+      for (int c = 0; c < 5; c++) v[5 + c] += pp[c];
+    }
+#pragma unroll
+  for (int c = 0; c < 10; c++) v[c] = warp_sum(v[c]);
+  if (lane == 0)
+#pragma unroll
+    for (int c = 0; c < 10; c++) red[warp][c] = v[c];
+  __syncthreads();
+  if (tid == 0) {
+    double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < 8; w++)
+      for (int c = 0; c < 10; c++) s[c] += red[w][c];
+    lml[b] = -0.5 * n * 1.8378770664093454835606594728112 - s[0] - 0.5 * s[1];
+    if (want_grad) {
+      const double *th = theta + b * ts;
+      grad[b * ts + 0] = th[0] * s[5];                 // 0.5 sum M * 2 alpha k
+      grad[b * ts + 1] = 0.5 * th[0] * th[0] * s[6];   // 0.5 sum M * alpha^2 dk/dl
+      for (int q = 0; q < nblocks; q++) grad[b * ts + 2 + q] = th[2 + q] * (s[2 + q] - s[7 + q]);
+    }
+  }
+}
+
+int launch_finalize_deriv(Handle *h, int n_grid, int nblocks, int np, int want_grad, const double *dvec, const double *z,
+                          const double *a, const double *partial, int ntasks, const double *theta, double *lml,
+                          double *grad, int batch) {
+  ProfScope ps__(h, PC_OTHER);
+  finalize_deriv_kernel<<<batch, 256, 0, h->stream>>>(n_grid, nblocks, np, want_grad, dvec, z, a, partial, ntasks, theta,
+                                                     lml, grad);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
 int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2) {
   ProfScope ps__(h, PC_OTHER);
   sumsq_logdiag_kernel<<<1, 256, 0, h->stream>>>(n, z, L, ldl, out2);

@@ -69,12 +69,16 @@ def sample_derivs_moments(params, ynoise, ti, handle=None):
     return h.gp_condition(K, KsK, KsKs, ynoise, sy * sy, 1e-8)
 
 
-def sample_derivs(params, ynoise, ti, rng=None, handle=None):
+def sample_derivs(params, ynoise, ti, rng=None, seed=None, handle=None):
     """pendulum_fit.R:227-255 including the MASS::mvrnorm(1, mu, Sigma) draw (:253): the draw is
-    mu + L z with L the GPU Cholesky factor of the posterior covariance and z ~ N(0, I) from `rng`."""
+    mu + L z with L the GPU Cholesky factor of the posterior covariance.  With `seed` the normals come
+    from the device generator (gpb200_mvrnorm: Philox, reproducible per seed); with `rng` (a NumPy
+    Generator) they are drawn on the host and only the factorisation and L z run on the GPU."""
     h = handle or capi.default_handle()
-    rng = rng or np.random.default_rng()
     mu, cov = sample_derivs_moments(params, ynoise, ti, handle=h)
+    if seed is not None:
+        return h.mvrnorm(1, mu, cov, int(seed))
+    rng = rng or np.random.default_rng()
     L = h.potrf(cov)
     return mu + h.trmv_lower(L, rng.standard_normal(mu.shape[0]))
 

@@ -144,6 +144,19 @@ GPB200_API int gpb200_lml_grad_batched(gpb200_handle_t h, int n, int B, const do
                             const double *y, long long y_stride, const double *theta,
                             double jitter, int want_grad, double *lml, double *grad, int *info);
 
+/* The same evaluation for a GP observed through derivatives (config C2; the dense-multi_normal LML of
+ * gpderivs.py:62-83 over the covdd kernel is order0 = 1, nblocks = 1; design_notes.Rmd:25-46 is the
+ * joint (y, y', y'') case order0 = 0, nblocks = 3).  On a grid t[n] the covariance is
+ *   K = alpha^2 {k_pq(t_i, t_j)}_{p,q = order0 .. order0+nblocks-1} + diag(noise_b^2 + jitter)
+ * with k_pq the kernels of derivative_kernels.R:39-73 (QQ..TT); it is (n*nblocks)^2, block b holding
+ * derivative order order0 + b, and y is the stacked observation vector of length n*nblocks.
+ * theta: B x (2 + nblocks) row-major = (alpha, rho, noise[0..nblocks)); grad has the same layout;
+ * t_stride / y_stride in doubles (0 = shared); lml[B], info[B]. */
+GPB200_API int gpb200_lml_grad_deriv_batched(gpb200_handle_t h, int n, int order0, int nblocks, int B,
+                                             const double *t, long long t_stride, const double *y,
+                                             long long y_stride, const double *theta, double jitter,
+                                             int want_grad, double *lml, double *grad, int *info);
+
 /* ---- a1-a3: the reference's one native entry point ----------------------------------------- */
 /* Exact twin of rbf_cov_chol (covariance.cpp:9-47): Sigma = exp(-(xi-xj)^2/(2 l^2)) + 1e-10 I,
  * L = chol(Sigma), dLdl = d L / d l (forward mode); both n x n column-major with zero strict
@@ -185,6 +198,20 @@ GPB200_API int gpb200_gp_condition(gpb200_handle_t h, int n, int m, const double
  * the block layout the reference uses: sigma is (ng+nd)^2 with the GIVEN block first. */
 GPB200_API int gpb200_cond_mvn(gpb200_handle_t h, int ng, int nd, const double *mean, const double *sigma,
                     int lds, const double *x_given, double *cond_mean, double *cond_var, int ldv);
+
+/* ---- f-4: posterior sampling ------------------------------------------------------------------ */
+/* out[e] = standard normal number (offset + e) of the stream `seed`, e in [0, len): counter-based
+ * Philox4x32-10 -> 53-bit uniforms -> Box-Muller (pairs: offset must be even).  Stateless, so any
+ * slice of a stream can be regenerated anywhere; replaces rnorm / numpy.random.randn on the host
+ * (ch2.py:43-45). */
+GPB200_API int gpb200_normal_fill(gpb200_handle_t h, unsigned long long seed, unsigned long long offset,
+                                  long long len, double *out);
+/* MASS::mvrnorm(n = ndraws, mu, Sigma) (pendulum_fit.R:253; lorenz.Rmd:105; `m + L z` of ch2.py:42-45):
+ * out is ndraws x m column-major (R's return layout; ldo >= ndraws), row d = mu + L z_d with
+ * L = chol(Sigma + jitter I) and z_d = normals [d*m, (d+1)*m) of gpb200_normal_fill(seed).  mu may be
+ * NULL (zeros).  (MASS uses an eigen-decomposition square root; both give N(mu, Sigma) draws.) */
+GPB200_API int gpb200_mvrnorm(gpb200_handle_t h, int ndraws, int m, const double *mu, const double *Sigma, int lds,
+                              double jitter, unsigned long long seed, double *out, int ldo);
 
 /* ---- (e) multi-GPU block-cyclic Cholesky of ONE large matrix: per-rank building blocks ------------
  * DEVICE pointers only.  A panel is a block column of the padded matrix (np = ceil(n/128)*128)

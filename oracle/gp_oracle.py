@@ -314,17 +314,100 @@ def rk_QQard(X, Y, phi):  # R/kernels.R:19 ; phi = (alpha, rho[D] or scalar)
 _JOINT = [["QQ", "QR", "QT"], ["RQ", "RR", "RT"], ["TQ", "TR", "TT"]]
 
 
-def gram_deriv(t, alpha, rho, noise, jitter, nblocks=3):
+def gram_deriv(t, alpha, rho, noise, jitter, nblocks=3, order0=0):
+    """order0 > 0 starts the stack at a higher derivative order (order0 = 1, nblocks = 1 is the
+    covdd-only covariance of gpderivs.py:62-81)."""
     t = np.asarray(t, dtype=np.float64)
     n = t.shape[0]
     K = np.empty((nblocks * n, nblocks * n))
     for bi in range(nblocks):
         for bj in range(nblocks):
-            K[bi * n:(bi + 1) * n, bj * n:(bj + 1) * n] = alpha ** 2 * outer_kernel(_JOINT[bi][bj], t, t, rho)
+            K[bi * n:(bi + 1) * n, bj * n:(bj + 1) * n] = alpha ** 2 * outer_kernel(_JOINT[order0 + bi][order0 + bj], t, t, rho)
     for bi in range(nblocks):
         idx = np.arange(bi * n, (bi + 1) * n)
         K[idx, idx] += noise[bi] ** 2 + jitter
     return K
+
+
+# d/dl of the nine kernels, written out term by term from the closed forms above
+# (d e / d l = e d^2 / l^3).  Checked against central differences in tests/test_oracle.py.
+def _dl_terms(tj, tk, l):
+    e, d = _e(tj, tk, l)
+    return e, d
+
+
+def ddl_QQ(tj, tk, l):
+    e, d = _dl_terms(tj, tk, l)
+    return e * d ** 2 / l ** 3
+
+
+def ddl_QR(tj, tk, l):
+    e, d = _dl_terms(tj, tk, l)
+    return e * d ** 3 / l ** 5 - 2.0 * e * d / l ** 3
+
+
+def ddl_RR(tj, tk, l):
+    e, d = _dl_terms(tj, tk, l)
+    return -2.0 * e / l ** 3 + 5.0 * e * d ** 2 / l ** 5 - e * d ** 4 / l ** 7
+
+
+def ddl_RT(tj, tk, l):
+    e, d = _dl_terms(tj, tk, l)
+    return -12.0 * e * d / l ** 5 + 9.0 * e * d ** 3 / l ** 7 - e * d ** 5 / l ** 9
+
+
+def ddl_TT(tj, tk, l):
+    e, d = _dl_terms(tj, tk, l)
+    return -12.0 * e / l ** 5 + 39.0 * e * d ** 2 / l ** 7 - 14.0 * e * d ** 4 / l ** 9 + e * d ** 6 / l ** 11
+
+
+DERIV_KERNELS_DL = {"QQ": ddl_QQ, "QR": ddl_QR, "RQ": lambda a, b, l: ddl_QR(b, a, l), "RR": ddl_RR,
+                    "QT": lambda a, b, l: -ddl_RR(a, b, l), "TQ": lambda a, b, l: -ddl_RR(b, a, l),
+                    "RT": ddl_RT, "TR": lambda a, b, l: ddl_RT(b, a, l), "TT": ddl_TT}
+
+
+def lml_grad_deriv(t, y, alpha, rho, noise, jitter=0.0, nblocks=None, order0=0):
+    """LML of the stacked derivative observations y ~ N(0, gram_deriv(...)) and its gradient with
+    respect to (alpha, rho, noise[0..nblocks)): what Stan's reverse sweep returns for the dense
+    multi_normal model of gpderivs.py:62-83 (there in the (sf2, l2, s2) parametrisation, see
+    gpderivs_log_prob_grad) and for the joint covariance of design_notes.Rmd:25-46."""
+    t = np.asarray(t, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+    noise = np.atleast_1d(np.asarray(noise, dtype=np.float64))
+    if nblocks is None:
+        nblocks = noise.shape[0]
+    n = t.shape[0]
+    N = n * nblocks
+    K = gram_deriv(t, alpha, rho, noise, jitter, nblocks, order0)
+    L = cholesky_decompose(K)
+    z = mdivide_left_tri_low(L, y)
+    a = sla.solve_triangular(L, z, lower=True, trans="T", check_finite=False)
+    val = -0.5 * N * LOG_TWO_PI - np.sum(np.log(np.diag(L))) - 0.5 * float(z @ z)
+    Kinv = sla.cho_solve((L, True), np.eye(N), check_finite=False)
+    M = np.outer(a, a) - Kinv
+    Kk = np.empty((N, N)); dK = np.empty((N, N))
+    for bi in range(nblocks):
+        for bj in range(nblocks):
+            name = _JOINT[order0 + bi][order0 + bj]
+            sl = (slice(bi * n, (bi + 1) * n), slice(bj * n, (bj + 1) * n))
+            Kk[sl] = outer_kernel(name, t, t, rho)
+            dK[sl] = DERIV_KERNELS_DL[name](t[:, None], t[None, :], rho)
+    g = np.empty(2 + nblocks)
+    g[0] = 0.5 * float(np.sum(M * (2.0 * alpha * Kk)))
+    g[1] = 0.5 * float(np.sum(M * (alpha ** 2 * dK)))
+    for b in range(nblocks):
+        g[2 + b] = 0.5 * 2.0 * noise[b] * float(np.trace(M[b * n:(b + 1) * n, b * n:(b + 1) * n]))
+    return float(val), g
+
+
+def gpderivs_log_prob_grad(t, dx, sf2, l2, s2):
+    """The likelihood term of the reference's Stan model in gpderivs.py:62-83:
+    Sigma = sf2 * covdd(t_i, t_j, l2) + s2 I, dx ~ multi_normal(0, Sigma), with
+    covdd = 2 exp(-d^2/l2) (l2 - 2 d^2) / l2^2 (gpderivs.py:35-37), i.e. the RR kernel with
+    alpha^2 = sf2, l^2 = l2 / 2, sigma^2 = s2.  Returns the log density (with constants) and its
+    gradient in (sf2, l2, s2) by the chain rule."""
+    alpha, l, sigma = np.sqrt(sf2), np.sqrt(l2 / 2.0), np.sqrt(s2)
+    v, g = lml_grad_deriv(t, dx, alpha, l, [sigma], 0.0, 1, 1)
+    return v, np.array([g[0] / (2.0 * alpha), g[1] / (4.0 * l), g[2] / (2.0 * sigma)])
 
 
 # --------------------------------------------------------------------------------------------------

@@ -48,13 +48,23 @@ p_Xn <- function(tn, Xn, phi_n, sigma_n) {
 }
 
 # ---- pendulum_fit.R:227-255 -----------------------------------------------------------------------
-sample_derivs <- function(params, ynoise, ti) {
+sample_derivs <- function(params, ynoise, ti, seed = NULL) {
   l <- params[1]; a <- params[2]; sy <- params[3]
   K <- gp_outer("QQ", ti, ti, l, a^2); KsK <- gp_outer("RQ", ti, ti, l, a^2); KsKs <- gp_outer("RR", ti, ti, l, a^2)
   m <- .Call("gp_condition", K, KsK, KsKs, as.double(ynoise), sy^2, 1e-8)
+  if (!is.null(seed)) return(as.numeric(.Call("gp_mvrnorm", 1L, m$mu, m$cov, as.double(seed))))  # device RNG
   L <- .Call("gp_potrf", m$cov)
   as.numeric(m$mu + L %*% rnorm(length(m$mu)))
+}
+mvrnorm <- function(n = 1, mu, Sigma, seed = sample.int(.Machine$integer.max, 1)) {   # MASS::mvrnorm signature + seed
+  out <- .Call("gp_mvrnorm", as.integer(n), as.double(mu), Sigma, as.double(seed))
+  if (n == 1) drop(out) else out
 }
 
 # ---- batched LML + gradient over hyper-parameter draws (the mclapply axis, pendulum_fit.R:259-268) -
 gp_lml_grad_draws <- function(x, y, theta, jitter = 0) .Call("gp_lml_grad_draws", as.double(x), as.double(y), theta, as.double(jitter))
+
+# ---- GP observed through derivatives (the Stan model inside gpderivs.py:25-133; design_notes.Rmd:25-46) ----
+# theta: (2 + nblocks) x B matrix, columns (alpha, rho, noise_1..noise_nblocks); y = c(y, yp, ypp) stacked
+gp_lml_grad_deriv_draws <- function(t, y, theta, order0 = 0L, jitter = 0)
+  .Call("gp_lml_grad_deriv_draws", as.double(t), as.double(y), theta, as.integer(order0), as.double(jitter))

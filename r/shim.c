@@ -196,6 +196,36 @@ SEXP gp_lml_grad_draws(SEXP x, SEXP y, SEXP theta, SEXP jitter) {
   return out;
 }
 
+/* LML + gradient of a GP observed through derivative orders order0 .. order0+nblocks-1 on the grid t
+ * (gpderivs.py:62-83 is order0 = 1, nblocks = 1; design_notes.Rmd:25-46 is 0, 3); theta is a
+ * (2 + nblocks) x B matrix (alpha, rho, noise[nblocks] per column), y the stacked observations */
+SEXP gp_lml_grad_deriv_draws(SEXP t, SEXP y, SEXP theta, SEXP order0, SEXP jitter) {
+  const int n = LENGTH(t), B = Rf_ncols(theta), nb = Rf_nrows(theta) - 2;
+  if (nb < 1 || LENGTH(y) != n * nb) Rf_error("gp_lml_grad_deriv_draws: y must hold n * (nrow(theta) - 2) values");
+  SEXP lml = PROTECT(Rf_allocVector(REALSXP, B));
+  SEXP grad = PROTECT(Rf_allocMatrix(REALSXP, 2 + nb, B));
+  SEXP info = PROTECT(Rf_allocVector(INTSXP, B));
+  check(gpb200_lml_grad_deriv_batched(handle(), n, Rf_asInteger(order0), nb, B, REAL(t), 0, REAL(y), 0, REAL(theta),
+                                      Rf_asReal(jitter), 1, REAL(lml), REAL(grad), INTEGER(info)), "lml_grad_deriv_draws");
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 3));
+  SET_VECTOR_ELT(out, 0, lml); SET_VECTOR_ELT(out, 1, grad); SET_VECTOR_ELT(out, 2, info);
+  SET_STRING_ELT(nm, 0, Rf_mkChar("lml")); SET_STRING_ELT(nm, 1, Rf_mkChar("grad")); SET_STRING_ELT(nm, 2, Rf_mkChar("info"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(5);
+  return out;
+}
+
+/* MASS::mvrnorm(n, mu, Sigma) with the device generator (pendulum_fit.R:253): n x length(mu) matrix */
+SEXP gp_mvrnorm(SEXP n_, SEXP mu, SEXP Sigma, SEXP seed) {
+  const int nd = Rf_asInteger(n_), m = Rf_nrows(Sigma);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, nd, m));
+  check(gpb200_mvrnorm(handle(), nd, m, REAL(mu), REAL(Sigma), m, 0.0, (unsigned long long)Rf_asReal(seed), REAL(out), nd > 0 ? nd : 1),
+        "mvrnorm");
+  UNPROTECT(1);
+  return out;
+}
+
 /* mu = Ks (K + s2 I)^-1 y ; cov = Kss - Ks (K + s2 I)^-1 Ks^T + jitter I   [pendulum_fit.R:242-251] */
 SEXP gp_condition(SEXP K, SEXP Ks, SEXP Kss, SEXP y, SEXP noise_var, SEXP jitter) {
   const int n = Rf_nrows(K), m = Rf_nrows(Ks);
@@ -235,6 +265,7 @@ static const R_CallMethodDef call_methods[] = {
     {"gp_condition", (DL_FUNC)&gp_condition, 6},       {"gp_cond_mvn", (DL_FUNC)&gp_cond_mvn, 4},
     {"gp_rbf_cov_chol_grid", (DL_FUNC)&gp_rbf_cov_chol_grid, 2}, {"gp_approx_L_basis", (DL_FUNC)&gp_approx_L_basis, 5},
     {"gp_se_chol_tangent", (DL_FUNC)&gp_se_chol_tangent, 5},
+    {"gp_lml_grad_deriv_draws", (DL_FUNC)&gp_lml_grad_deriv_draws, 5}, {"gp_mvrnorm", (DL_FUNC)&gp_mvrnorm, 4},
     {NULL, NULL, 0}};
 
 void R_init_gpb200_r(DllInfo *dll) {

@@ -129,3 +129,24 @@ def test_westbrook_real_inputs(handle, westbrook):
     K6 = o.gram_se(x, 1.0, 0.3, 1e-6)
     L = handle.potrf(K6)
     assert np.linalg.norm(L @ L.T - K6) / np.linalg.norm(K6) < 20 * 1438 * EPS
+
+
+def test_c2_joint_derivative_lml_and_gradient_n512(handle):
+    # C2 at full size: LML + gradient in (alpha, rho, noise_y, noise_yp, noise_ypp) of the 1536^2 joint
+    # covariance (design_notes.Rmd:25-46), batched over 3 draws; oracle on one of them
+    t = np.linspace(0, 10, 512)
+    rng = np.random.default_rng(2)
+    noise = np.array([0.1, 0.2, 0.4])
+    yy = np.concatenate([np.sin(t), np.cos(t), -np.sin(t)]) + np.repeat(noise, 512) * rng.standard_normal(1536)
+    th = np.array([[1.0, 1.3, 0.1, 0.2, 0.4], [0.8, 1.0, 0.15, 0.2, 0.3], [1.4, 1.6, 0.1, 0.3, 0.5]])
+    lml, grad, info = handle.lml_grad_deriv_batched(t, yy, th, 1e-6)
+    assert np.all(info == 0)
+    rv, rg = o.lml_grad_deriv(t, yy, th[1, 0], th[1, 1], th[1, 2:], 1e-6)
+    assert abs(lml[1] - rv) <= 1e-9 * abs(rv) and relerr(grad[1], rg) < 1e-9
+    # LML agrees with the separately assembled route gram_deriv -> potrf -> mvn_chol_lpdf
+    K = handle.gram_deriv(t, th[0, 0], th[0, 1], th[0, 2:], 1e-6, nblocks=3)
+    lp = handle.mvn_chol_lpdf(yy, None, handle.potrf(K))
+    assert abs(lml[0] - lp) <= 1e-11 * abs(lp)
+    # batching changes no bit
+    l1, g1, _ = handle.lml_grad_deriv_batched(t, yy, th[2:3], 1e-6)
+    assert l1[0] == lml[2] and np.array_equal(g1[0], grad[2])

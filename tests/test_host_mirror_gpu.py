@@ -5,6 +5,7 @@ seq(-2, 2, 0.2), exp(t) data, then numeric comparison with the CPU oracle."""
 import numpy as np
 import pytest
 
+from gp_b200 import capi
 from oracle import gp_oracle as o
 
 pytestmark = pytest.mark.gpu
@@ -208,3 +209,58 @@ def test_map_fit_recovers_noise_level(handle):
         up, um = u.copy(), u.copy(); up[k] += h; um[k] -= h
         fd = (o.lp_fit_hyperparameters(t, y, *up) - o.lp_fit_hyperparameters(t, y, *um)) / (2 * h)
         assert abs(fd) < 5e-2
+
+
+# ---- f-4: device RNG and mvrnorm (pendulum_fit.R:253, lorenz.Rmd:105, ch2.py:42-45) -----------------
+def test_device_normals_match_the_restated_stream(handle):
+    from oracle import philox
+    z = handle.normal_fill(1234, 100001)
+    ref = philox.normals(1234, 100001)
+    assert np.max(np.abs(z - ref)) < 1e-13          # same integers; log / sincos differ by ulps at most
+    assert np.array_equal(handle.normal_fill(1234, 500, offset=4000), z[4000:4500])
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+    with pytest.raises(capi.GpB200Error):
+        handle.normal_fill(1, 10, offset=3)
+
+
+@pytest.mark.parametrize("m,ndraws", [(1, 1), (25, 1), (100, 7), (300, 130)])
+def test_mvrnorm_is_mean_plus_chol_times_the_stream(handle, m, ndraws):
+    from oracle import philox
+    rng = np.random.default_rng(m)
+    x = np.sort(rng.uniform(0, 5, m))
+    S = o.gram_se(x, 1.3, 0.7, 0.05)
+    mu = rng.standard_normal(m)
+    out = handle.mvrnorm(ndraws, mu, S, seed=99)
+    L = o.cholesky_decompose(S)
+    Z = philox.normals(99, m * ndraws).reshape(ndraws, m)
+    ref = mu[None, :] + Z @ L.T
+    got = out[None, :] if ndraws == 1 else out
+    assert got.shape == (ndraws, m)
+    assert np.max(np.abs(got - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref)))
+    assert not np.array_equal(handle.mvrnorm(ndraws, mu, S, seed=100), out)
+
+
+def test_mvrnorm_moments_and_errors(handle):
+    rng = np.random.default_rng(0)
+    m, nd = 48, 20000
+    A = rng.standard_normal((m, m))
+    S = A @ A.T / m + 0.1 * np.eye(m)
+    mu = np.linspace(-1, 1, m)
+    X = handle.mvrnorm(nd, mu, S, seed=7)
+    assert np.max(np.abs(X.mean(0) - mu)) < 5 * np.sqrt(np.max(np.diag(S)) / nd)
+    C = np.cov(X.T)
+    assert np.max(np.abs(C - S)) < 0.06 * np.max(np.abs(S))
+    with pytest.raises(capi.NotPositiveDefiniteError):
+        handle.mvrnorm(2, None, -np.eye(3), seed=1)
+
+
+def test_sample_derivs_with_device_rng(handle, golden):
+    from gp_b200 import ode_gp_library as lib
+    t, y = golden["ts"], golden["y"]
+    d1 = lib.sample_derivs((1.0, 1.0, 0.1), y, t, seed=5, handle=handle)
+    d2 = lib.sample_derivs((1.0, 1.0, 0.1), y, t, seed=5, handle=handle)
+    d3 = lib.sample_derivs((1.0, 1.0, 0.1), y, t, seed=6, handle=handle)
+    mu, cov = lib.sample_derivs_moments((1.0, 1.0, 0.1), y, t, handle=handle)
+    assert np.array_equal(d1, d2) and not np.array_equal(d1, d3)
+    # a draw lies within a few posterior sd of the posterior mean
+    assert np.max(np.abs(d1 - mu) / np.sqrt(np.diag(cov))) < 6.0

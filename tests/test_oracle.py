@@ -180,3 +180,51 @@ def test_westbrook_fixture_shape(westbrook):
     assert x.shape == (1438,) and len(np.unique(x)) == 1073 and abs(x.min() + 0.4976) < 1e-3 and x.max() == 0.5
     # duplicated inputs: the exact-GP Gram is singular without jitter (SURVEY 2.1 "Data")
     assert o.potrf_info(o.gram_se(x, 1.0, 0.3, 0.0)) > 0
+
+
+# ---- derivative-observation LML (gpderivs.py:62-83; design_notes.Rmd:25-46) ------------------------
+def test_kernel_length_scale_derivatives_match_central_differences():
+    rng = np.random.default_rng(0)
+    a = rng.uniform(0, 3, 64); b = rng.uniform(0, 3, 64)
+    l, h = 0.9, 1e-6
+    for name, f in o.DERIV_KERNELS.items():
+        fd = (f(a, b, l + h) - f(a, b, l - h)) / (2 * h)
+        an = o.DERIV_KERNELS_DL[name](a, b, l)
+        assert np.max(np.abs(fd - an)) <= 1e-8 * np.max(np.abs(an)), name
+
+
+def test_lml_grad_deriv_gradient_vs_finite_differences_and_reference_parametrisation():
+    rng = np.random.default_rng(1)
+    t = np.linspace(0, 5, 40)
+    y = np.concatenate([np.sin(t), np.cos(t), -np.sin(t)]) + 0.1 * rng.standard_normal(120)
+    th = np.array([1.2, 0.8, 0.1, 0.2, 0.3])
+    v, g = o.lml_grad_deriv(t, y, th[0], th[1], th[2:], 1e-6)
+    for i in range(5):
+        tp = th.copy(); tm = th.copy(); tp[i] += 1e-6; tm[i] -= 1e-6
+        fd = (o.lml_grad_deriv(t, y, tp[0], tp[1], tp[2:], 1e-6)[0] - o.lml_grad_deriv(t, y, tm[0], tm[1], tm[2:], 1e-6)[0]) / 2e-6
+        assert abs(fd - g[i]) <= 1e-6 * max(1.0, abs(g[i]))
+    # the reference's own covdd in its l2 parametrisation (gpderivs.py:35-37), typed out literally
+    sf2, l2, s2 = 1.3, 2.2, 0.04
+    d = t[:, None] - t[None, :]
+    Sigma = sf2 * 2 * np.exp(-d ** 2 / l2) * (l2 - 2 * d ** 2) / l2 ** 2 + s2 * np.eye(40)
+    dx = np.cos(t) + 0.15 * rng.standard_normal(40)
+    ref = -0.5 * (40 * np.log(2 * np.pi) + np.linalg.slogdet(Sigma)[1] + dx @ np.linalg.solve(Sigma, dx))
+    v, g = o.gpderivs_log_prob_grad(t, dx, sf2, l2, s2)
+    assert abs(v - ref) <= 1e-10 * abs(ref)
+    for i, hh in enumerate(np.eye(3) * 1e-6):
+        fd = (o.gpderivs_log_prob_grad(t, dx, *(np.array([sf2, l2, s2]) + hh))[0] -
+              o.gpderivs_log_prob_grad(t, dx, *(np.array([sf2, l2, s2]) - hh))[0]) / 2e-6
+        assert abs(fd - g[i]) <= 1e-6 * max(1.0, abs(g[i]))
+
+
+# ---- f-4: the device random-number stream restated (oracle/philox.py) -------------------------------
+def test_philox_known_answer_and_normal_moments():
+    from oracle import philox
+    # Random123 known-answer vector: philox4x32-10, counter = 0, key = 0
+    r = philox.philox4x32_10(np.array([0], dtype=np.uint64), 0)
+    assert [int(v) for v in r[0]] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    z = philox.normals(42, 200001)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3.0) < 0.06
+    assert np.array_equal(philox.normals(42, 100, offset=1000), philox.normals(42, 1100)[1000:])
+    assert not np.array_equal(philox.normals(43, 100), z[:100])
