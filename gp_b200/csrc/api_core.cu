@@ -28,6 +28,8 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return -1000; }
+  const char *gc = getenv("GPB200_GEMM_CFG");  // tuning knob, same meaning as gpb200_set_gemm_config
+  if (gc && gc[0] >= '0' && gc[0] <= '4') h->gemm_cfg_override = gc[0] - '0';
   const char *ng = getenv("GPB200_NO_GRAPH");
   if (ng && ng[0] == '1') h->graphs_enabled = 0;
   *out = h;
@@ -80,7 +82,7 @@ extern "C" int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles) {
 
 // test/tuning knob: 0 automatic, 1 force the 8-warp GEMM configuration, 2 force the 16-warp zero-skipping one
 extern "C" int gpb200_set_gemm_config(gpb200_handle_t h, int cfg) {
-  if (!h || cfg < 0 || cfg > 2) return -1;
+  if (!h || cfg < 0 || cfg > 4) return -1;
   h->gemm_cfg_override = cfg;
   return 0;
 }

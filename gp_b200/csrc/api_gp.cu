@@ -25,10 +25,11 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
   TaskList tl;
   RC(tasks_lauum(h, nt, &tl));
   const int ntasks = tl.count(0);
+  const int nparts = ntasks * 2;  // trace partial records per item: one per CTA, at most two CTAs per tile
 
   // chunk the batch so that the resident set fits the workspace limit.  cudaMemGetInfo costs
   // milliseconds with tens of GB allocated, so it is only consulted when the workspace must grow.
-  const size_t per_item = pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)ntasks * pw * 8) + 64;
+  const size_t per_item = pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)nparts * pw * 8) + 64;
   const size_t fixed = pad256((size_t)B * (x_stride ? ng : 0) * 8 + ng * 8) + pad256((size_t)B * (y_stride ? n : 0) * 8 + n * 8) +
                        2 * pad256((size_t)B * ts * 8) + pad256((size_t)B * 8) + pad256((size_t)B * 4) + 4096;
   int Bc = B;
@@ -54,7 +55,7 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
   int *dinfo = a.take<int>(B);
   double *Lbuf = a.take<double>((size_t)Bc * mat), *Sbuf = a.take<double>((size_t)Bc * mat);
   double *zbuf = a.take<double>((size_t)Bc * np), *abuf = a.take<double>((size_t)Bc * np), *dvec = a.take<double>((size_t)Bc * np);
-  double *partial = a.take<double>((size_t)Bc * ntasks * pw);
+  double *partial = a.take<double>((size_t)Bc * nparts * pw);
   if (!partial) BAD_ARG(h, 1002, "lml_grad_batched: workspace arithmetic error");
 
   // The kernel sequence (everything between staging the inputs and reading the outputs).
@@ -91,10 +92,10 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
         else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
       }
       if (sp.deriv)
-        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0,
+        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, gemm_small_k(np)), cth, dlml + b0,
                                  dgrad + (long long)b0 * ts, bc));
       else
-        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks, cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
+        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, gemm_small_k(np)), cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
     }
     return 0;
   };
@@ -121,7 +122,7 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
       long long jbits;
       memcpy(&jbits, &jitter, sizeof(jbits));
       const std::vector<long long> key = {n, B, want_grad, xs, ys, jbits, (long long)(uintptr_t)h->ws, h->chol_panel_override,
-                                          sp.deriv, sp.order0, sp.nblocks};
+                                          sp.deriv, sp.order0, sp.nblocks, h->gemm_cfg_override};
       auto it = h->graphs.find(key);
       if (it == h->graphs.end()) {
         // task lists allocate and synchronise on first use: make sure they exist before the capture

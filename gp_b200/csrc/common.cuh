@@ -62,7 +62,7 @@ struct Handle {
   long long launches = 0;
   long long ws_limit = 0;
   int chol_panel_override = 0;
-  int gemm_cfg_override = 0;  // 0 auto, 1 force the 8-warp configuration, 2 force the 16-warp zero-skipping one
+  int gemm_cfg_override = 0;  // 0 auto, 1 force Big (8 warps, 1 CTA/SM), 2 Small (16 warps, zero-skipping), 3 Half (128x64, 2 CTAs/SM)
   char err[512] = {0};
   // grow-only device workspace
   void *ws = nullptr;
@@ -143,6 +143,7 @@ enum GemmEpi { EPI_AXPBY = 0, EPI_TRACE = 1, EPI_TRACE_DERIV = 2 };
 
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch);
 int gemm_smem_setup(Handle *h);
+int gemm_nsplit(const Handle *h, int small_k);
 
 // panel kernels (panel.cu)
 int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n,

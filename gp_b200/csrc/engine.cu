@@ -139,15 +139,18 @@ int tasks_trtri(Handle *h, int nt, TaskList *s_out, TaskList *w_out) {
   return upload_tasks(h, kw, tw, ow, w_out);
 }
 
-// G = W^T W, lower tiles: G[i,j] = sum_{k>=i} W[k,i]^T W[k,j]
+// G = W^T W, one tile per unordered pair: G[j,i] = sum_{k>=i} W[k,j]^T W[k,i] for j <= i, i.e. the UPPER
+// tiles (the transposes of the lower ones; the only consumer is the symmetric trace epilogue, nothing
+// is stored).  Written this way the triangular operand tile W[i,i] is the B operand, whose zero half
+// the column-split GEMM configurations skip for a whole CTA.
 int tasks_lauum(Handle *h, int nt, TaskList *out) {
   const long long key = tkey(TK_LAUUM, nt);
   if (cached(h, key, out)) return 0;
   std::vector<TileTask> t;
   for (int i = 0; i < nt; i++)
     for (int j = 0; j <= i; j++)
-      t.push_back({i * TILE, i * TILE, i * TILE, j * TILE, i * TILE, j * TILE, (nt - i) * TILE,
-                   TF_A_TRI_FIRST | (i == j ? (TF_DIAG | TF_B_TRI_FIRST) : 0)});
+      t.push_back({i * TILE, j * TILE, i * TILE, i * TILE, j * TILE, i * TILE, (nt - i) * TILE,
+                   TF_B_TRI_FIRST | (i == j ? (TF_DIAG | TF_A_TRI_FIRST) : 0)});
   sort_desc(t, 0);
   std::vector<int> off = {0, (int)t.size()};
   return upload_tasks(h, key, t, off, out);

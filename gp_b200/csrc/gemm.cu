@@ -18,32 +18,50 @@
 //   TN  G = W^T W  + fused trace epilogue  0.5 tr((a a^T - K^-1) dK/dtheta)  (the reverse sweep
 //                               of multi_normal_cholesky -> cholesky_decompose -> cov_exp_quad)
 #include "common.cuh"
+#include "fastexp.cuh"
 
 namespace gpb {
 
+#ifndef GPB_DEFAULT_CFG
+#define GPB_DEFAULT_CFG 4
+#endif
 constexpr int KC = 16;
-constexpr int STAGES = 4;
-// Two configurations of the same kernel are built:
-//   Big   2x4 warps of 64x32, no zero-skipping       -- long k-loops (nt > 12): fewest fragment loads per DMMA
-//   Small 4x4 warps of 32x32, triangular zero-skip   -- short k-loops, where the diagonal tiles of
-//         triangular operands are a large share of the work (19 % of the executed flops at N=1024)
-template <int WARPS_M_, int WARPS_N_, bool SKIP_>
+// Four configurations of the same kernel are built (gpb200_set_gemm_config; 4 is the default):
+//   1 Big    128x128 CTA tile, 2x4 warps of 64x32, 4 stages, 1 CTA/SM
+//   2 Small  128x128, 4x4 warps of 32x32, per-warp zero-skipping of triangular operand tiles
+//   3 Half   128x64 CTA tile, 2x2 warps of 64x32, 3 stages, 2 CTAs/SM
+//   4 Half8  128x64 CTA tile, 4x2 warps of 32x32, 3 stages, 2 CTAs/SM  <- default
+// With one CTA per SM every per-chunk barrier, prologue and epilogue is a bubble in the DMMA pipe
+// (91.5 % active, profiles/ncu_summary_r01b.md).  Two independent half-tile CTAs per SM cover each
+// other's bubbles (96 %), and with 32x32 warp tiles each sub-partition still has two warps of the other
+// CTA to draw DMMAs from while one CTA sits in a barrier or in its epilogue.  Splitting the tile along n
+// also makes the zero half of a triangular B operand tile skippable for a whole CTA (no warp imbalance).
+template <int WARPS_M_, int WARPS_N_, bool SKIP_, int TN_ = TILE, int STAGES_ = 4, int MINB_ = 1>
 struct GemmCfg {
-  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;  // warp grid over the 128x128 CTA tile
-  static constexpr int WM = TILE / WARPS_M_, WN = TILE / WARPS_N_;  // warp tile
+  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;  // warp grid over the TILE x TN CTA tile
+  static constexpr int TN = TN_;                                // CTA tile extent in n (TILE in m)
+  static constexpr int NSPLIT = TILE / TN_;                     // CTAs per 128x128 task
+  static constexpr int WM = TILE / WARPS_M_, WN = TN_ / WARPS_N_;  // warp tile
   static constexpr int MI = WM / 8, NI = WN / 8;                // 8x8 mma tiles per warp
   static constexpr int NTHREADS = 32 * WARPS_M_ * WARPS_N_;
-  static constexpr int NCOPY = KC * TILE / 2 / NTHREADS;        // 16-byte copies per thread per operand per stage
+  static constexpr int NCOPY_A = KC * TILE / 2 / NTHREADS;      // 16-byte copies per thread per stage
+  static constexpr int NCOPY_B = KC * TN_ / 2 / NTHREADS;
   static constexpr bool SKIP = SKIP_;
+  static constexpr int STAGES = STAGES_, MINB = MINB_;
+  static constexpr int LD_MC_B = TN_ + 4;                       // B stage with n contiguous: [KC][TN+4]
+  static constexpr int STAGE_A = TILE * (KC + 4);               // 2560 doubles >= KC * (TILE + 4)
+  static constexpr int STAGE_B = TN_ * (KC + 4);                // >= KC * (TN + 4)
+  static constexpr int SMEM_BYTES = STAGES_ * (STAGE_A + STAGE_B) * (int)sizeof(double);
 };
 using CfgBig = GemmCfg<2, 4, false>;
+using CfgHalf = GemmCfg<2, 2, false, 64, 3, 2>;
+using CfgHalf8 = GemmCfg<4, 2, false, 64, 3, 2>;
 using CfgSmall = GemmCfg<4, 4, true>;
 constexpr int LD_MC = TILE + 4;  // operand with the tile index contiguous: stage[KC][132]
 constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
-constexpr int STAGE_DOUBLES = TILE * LD_KC;  // 2560 >= KC * LD_MC = 2112
 constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 5 * 16 + 8;
-constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_DOUBLES * (int)sizeof(double);  // 163840 (the trace epilogue's scratch reuses it)
-static_assert(EPI_SCRATCH_DOUBLES <= STAGES * 2 * STAGE_DOUBLES, "epilogue scratch must fit the pipeline buffers");
+static_assert(EPI_SCRATCH_DOUBLES * 8 <= CfgHalf::SMEM_BYTES, "epilogue scratch must fit the pipeline buffers");
+static_assert((CfgHalf::LD_MC_B % 16) == 4 && (LD_MC % 16) == 4 && (LD_KC % 16) == 4, "conflict-free fragment loads");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -60,11 +78,26 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 }
 
 template <class Cfg, bool A_KC, bool B_KC, int EPI>
-__global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(const GemmParams p) {
   constexpr int WARPS_N = Cfg::WARPS_N, WM = Cfg::WM, WN = Cfg::WN, MI = Cfg::MI, NI = Cfg::NI;
-  constexpr int NTHREADS = Cfg::NTHREADS, NCOPY = Cfg::NCOPY;
+  constexpr int NTHREADS = Cfg::NTHREADS, NCOPY_A = Cfg::NCOPY_A, NCOPY_B = Cfg::NCOPY_B;
+  constexpr int STAGES = Cfg::STAGES, TN = Cfg::TN, LD_MC_B = Cfg::LD_MC_B;
+  constexpr int STAGE_DOUBLES = Cfg::STAGE_A, STAGE_PAIR = Cfg::STAGE_A + Cfg::STAGE_B;
   extern __shared__ __align__(16) double smem[];
-  const TileTask task = p.tasks[blockIdx.x];
+  TileTask task = p.tasks[blockIdx.x / Cfg::NSPLIT];
+  const int n0 = (Cfg::NSPLIT > 1) ? (int)(blockIdx.x % Cfg::NSPLIT) * TN : 0;
+  if (Cfg::NSPLIT > 1) {  // this CTA owns columns [n0, n0 + TN) of the task's 128x128 tile
+    if (B_KC) task.b_c += n0; else task.b_r += n0;
+    task.c_c += n0;
+    // A triangular B operand tile is all zero over half of its k-range for one of the two column
+    // halves: that half simply contracts over 64 fewer k (uniform for the whole CTA).
+    if ((task.flags & TF_B_TRI_FIRST) && n0 >= TILE / 2) {  // zero where k_local < n_local: skip the first 64 k
+      if (A_KC) task.a_r += TILE / 2; else task.a_c += TILE / 2;
+      if (B_KC) task.b_r += TILE / 2; else task.b_c += TILE / 2;
+      task.k_len -= TILE / 2;
+    }
+    if ((task.flags & TF_B_TRI_LAST) && n0 < TILE / 2) task.k_len -= TILE / 2;  // zero where k_local > n_local
+  }
   const long long b = blockIdx.y;
   const double *__restrict__ A = p.A.p + b * p.A.stride;
   const double *__restrict__ Bm = p.B.p + b * p.B.stride;
@@ -85,11 +118,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
 
   const int nk = task.k_len / KC;
 
-  // per-thread copy descriptors: 4 x 16B for A and 4 x 16B for B per stage
-  const double *srcA[NCOPY], *srcB[NCOPY];
-  int dstA[NCOPY], dstB[NCOPY];
+  // per-thread copy descriptors: NCOPY_A x 16B for A and NCOPY_B x 16B for B per stage
+  const double *srcA[NCOPY_A], *srcB[NCOPY_B];
+  int dstA[NCOPY_A], dstB[NCOPY_B];
 #pragma unroll
-  for (int r = 0; r < NCOPY; r++) {
+  for (int r = 0; r < NCOPY_A; r++) {
     const int idx = tid + NTHREADS * r;
     if (!A_KC) {
       const int k = idx >> 6, m2 = idx & 63;
@@ -100,10 +133,14 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
       srcA[r] = A + (task.a_r + 2 * k2) + (long long)(task.a_c + m) * lda;
       dstA[r] = m * LD_KC + 2 * k2;
     }
+  }
+#pragma unroll
+  for (int r = 0; r < NCOPY_B; r++) {
+    const int idx = tid + NTHREADS * r;
     if (!B_KC) {
-      const int k = idx >> 6, n2 = idx & 63;
+      const int k = idx / (TN / 2), n2 = idx % (TN / 2);
       srcB[r] = Bm + (task.b_r + 2 * n2) + (long long)(task.b_c + k) * ldb;
-      dstB[r] = k * LD_MC + 2 * n2;
+      dstB[r] = k * LD_MC_B + 2 * n2;
     } else {
       const int n = idx >> 3, k2 = idx & 7;
       srcB[r] = Bm + (task.b_r + 2 * k2) + (long long)(task.b_c + n) * ldb;
@@ -116,13 +153,13 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
   // The source addresses are recomputed from constant bases for every chunk: incrementing the
   // registers an in-flight LDGSTS still reads costs a long-scoreboard (WAR) stall per chunk.
   auto load_stage = [&](int stage, int chunk) {
-    double *sA = smem + stage * 2 * STAGE_DOUBLES;
+    double *sA = smem + stage * STAGE_PAIR;
     double *sB = sA + STAGE_DOUBLES;
     const long long offA = (long long)chunk * stepA, offB = (long long)chunk * stepB;
 #pragma unroll
-    for (int r = 0; r < NCOPY; r++) cp_async16(sA + dstA[r], srcA[r] + offA);
+    for (int r = 0; r < NCOPY_A; r++) cp_async16(sA + dstA[r], srcA[r] + offA);
 #pragma unroll
-    for (int r = 0; r < NCOPY; r++) cp_async16(sB + dstB[r], srcB[r] + offB);
+    for (int r = 0; r < NCOPY_B; r++) cp_async16(sB + dstB[r], srcB[r] + offB);
   };
   auto load_frags = [&](const double *sA, const double *sB, int kk, double (&af)[MI], double (&bf)[NI]) {
 #pragma unroll
@@ -130,7 +167,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
       af[mi] = A_KC ? sA[(wm + mi * 8 + g) * LD_KC + kk * 4 + t] : sA[(kk * 4 + t) * LD_MC + wm + mi * 8 + g];
 #pragma unroll
     for (int ni = 0; ni < NI; ni++)
-      bf[ni] = B_KC ? sB[(wn + ni * 8 + g) * LD_KC + kk * 4 + t] : sB[(kk * 4 + t) * LD_MC + wn + ni * 8 + g];
+      bf[ni] = B_KC ? sB[(wn + ni * 8 + g) * LD_KC + kk * 4 + t] : sB[(kk * 4 + t) * LD_MC_B + wn + ni * 8 + g];
   };
 
   // prologue: all STAGES stages in flight, wait for chunk 0, first fragments in registers
@@ -153,14 +190,15 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
     const int kl = kc - (nk - TILE / KC);  // chunk index inside the LAST k-tile (>= 0 there)
     bool sk = false;
     if ((tflags & TF_A_TRI_FIRST) && kc < TILE / KC && kc * KC + KC - 1 < wm) sk = true;   // zero where k < m
-    if ((tflags & TF_B_TRI_FIRST) && kc < TILE / KC && kc * KC + KC - 1 < wn) sk = true;   // zero where k < n
+    const int wnt = n0 + wn;  // warp's first column inside the task's 128x128 tile
+    if ((tflags & TF_B_TRI_FIRST) && kc < TILE / KC && kc * KC + KC - 1 < wnt) sk = true;  // zero where k < n
     if ((tflags & TF_A_TRI_LAST) && kl >= 0 && kl * KC > wm + WM - 1) sk = true;           // zero where k > m
-    if ((tflags & TF_B_TRI_LAST) && kl >= 0 && kl * KC > wn + WN - 1) sk = true;           // zero where k > n
+    if ((tflags & TF_B_TRI_LAST) && kl >= 0 && kl * KC > wnt + WN - 1) sk = true;          // zero where k > n
     return sk;
   };
 
   for (int kc = 0; kc < nk; kc++) {
-    const double *sA = smem + (kc % STAGES) * 2 * STAGE_DOUBLES;
+    const double *sA = smem + (kc % STAGES) * STAGE_PAIR;
     const double *sB = sA + STAGE_DOUBLES;
     if (skip_chunk(kc)) {  // warp-uniform
       cp_async_wait<STAGES - 2>();
@@ -168,7 +206,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
       if (kc + STAGES < nk) load_stage(kc % STAGES, kc + STAGES);
       cp_async_commit();
       if (kc + 1 < nk) {
-        const double *nA = smem + ((kc + 1) % STAGES) * 2 * STAGE_DOUBLES;
+        const double *nA = smem + ((kc + 1) % STAGES) * STAGE_PAIR;
         load_frags(nA, nA + STAGE_DOUBLES, 0, af[0], bf[0]);
       }
       continue;
@@ -186,7 +224,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
         if (kc + STAGES < nk) load_stage(kc % STAGES, kc + STAGES);
         cp_async_commit();
         if (kc + 1 < nk) {
-          const double *nA = smem + ((kc + 1) % STAGES) * 2 * STAGE_DOUBLES;
+          const double *nA = smem + ((kc + 1) % STAGES) * STAGE_PAIR;
           load_frags(nA, nA + STAGE_DOUBLES, 0, af[nxt], bf[nxt]);
         }
       }
@@ -230,16 +268,13 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
     const int ng = p.n_grid;
     const double *x = p.x + b * p.x_stride;
     const double *av = p.avec + b * p.a_stride;
-    if (tid < TILE) {
-      const int i = task.c_r + tid;
+    for (int q = tid; q < TILE + TN; q += NTHREADS) {
+      const bool row = q < TILE;
+      const int ql = row ? q : q - TILE;
+      const int i = (row ? task.c_r : task.c_c) + ql;
       const int gi = i - (i >= ng ? ng : 0) - (i >= 2 * ng ? ng : 0);
-      xr[tid] = (i < p.n) ? x[gi] : 0.0;
-      ar[tid] = (i < p.n) ? av[i] : 0.0;
-    } else if (tid < 2 * TILE) {
-      const int j = task.c_c + tid - TILE;
-      const int gj = j - (j >= ng ? ng : 0) - (j >= 2 * ng ? ng : 0);
-      xc[tid - TILE] = (j < p.n) ? x[gj] : 0.0;
-      ac[tid - TILE] = (j < p.n) ? av[j] : 0.0;
+      (row ? xr : xc)[ql] = (i < p.n) ? x[gi] : 0.0;
+      (row ? ar : ac)[ql] = (i < p.n) ? av[i] : 0.0;
     }
     __syncthreads();
     const double l = p.theta[b * p.theta_stride + 1];
@@ -262,7 +297,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
             const int bi = (i >= ng) + (i >= 2 * ng);
             const int pi = p.order0 + bi, m = pi + p.order0 + bj;
             const double u = (xr[ml] - xc[nl]) * il;
-            const double ek = exp(-0.5 * u * u);
+            const double ek = exp_nonpos(-0.5 * u * u);
             double hp = 0.0, hc = 1.0, lp = 1.0, hm = 1.0, lm = 1.0, hm2 = 0.0;
 #pragma unroll
             for (int k = 1; k <= 6; k++) {
@@ -303,7 +338,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
     if (tid < 5) {
       double r = 0.0;
       for (int w8 = 0; w8 < NTHREADS / 32; w8++) r += red[w8 * 5 + tid];
-      p.partial[((long long)b * p.ntasks + blockIdx.x) * 8 + tid] = r;
+      p.partial[((long long)b * gridDim.x + blockIdx.x) * 8 + tid] = r;
     }
   } else {
     // ---- fused trace epilogue: this tile of G = K^-1 never has to reach HBM -----------------
@@ -312,14 +347,12 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
     double *red = smem + 4 * TILE;
     const double *x = p.x + b * p.x_stride;
     const double *av = p.avec + b * p.a_stride;
-    if (tid < TILE) {
-      const int i = task.c_r + tid;
-      xr[tid] = (i < p.n) ? x[i] : 0.0;
-      ar[tid] = (i < p.n) ? av[i] : 0.0;
-    } else if (tid < 2 * TILE) {
-      const int j = task.c_c + tid - TILE;
-      xc[tid - TILE] = (j < p.n) ? x[j] : 0.0;
-      ac[tid - TILE] = (j < p.n) ? av[j] : 0.0;
+    for (int q = tid; q < TILE + TN; q += NTHREADS) {
+      const bool row = q < TILE;
+      const int ql = row ? q : q - TILE;
+      const int i = (row ? task.c_r : task.c_c) + ql;
+      (row ? xr : xc)[ql] = (i < p.n) ? x[i] : 0.0;
+      (row ? ar : ac)[ql] = (i < p.n) ? av[i] : 0.0;
     }
     __syncthreads();
     const double rho = p.theta[b * 3 + 1];
@@ -341,7 +374,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
           if (i < p.n && j < p.n) {
             const double d = xr[ml] - xc[nl];
             const double d2 = d * d;
-            const double ek = exp(d2 * nh);
+            const double ek = exp_nonpos(d2 * nh);
             const double M = ar[ml] * ac[nl] - G;
             s_se += M * ek;
             s_d2 += M * ek * d2;
@@ -377,7 +410,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
         r1 += red[w8 * 3 + 1];
         r2 += red[w8 * 3 + 2];
       }
-      double *o = p.partial + ((long long)b * p.ntasks + blockIdx.x) * 4;
+      double *o = p.partial + ((long long)b * gridDim.x + blockIdx.x) * 4;
       o[0] = r0;
       o[1] = r1;
       o[2] = r2;
@@ -389,20 +422,20 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1) gemm_tile_kernel(const GemmP
 template <class Cfg, bool A_KC, bool B_KC, int EPI>
 static int launch_one(Handle *h, const GemmParams &p, int ntasks, int batch) {
   auto kern = gemm_tile_kernel<Cfg, A_KC, B_KC, EPI>;
-  dim3 grid(ntasks, batch);
+  dim3 grid(ntasks * Cfg::NSPLIT, batch);
   ProfScope ps__(h, PC_GEMM);
-  kern<<<grid, Cfg::NTHREADS, GEMM_SMEM_BYTES, h->stream>>>(p);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, h->stream>>>(p);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
 
 template <class Cfg>
 static int smem_setup_cfg(Handle *h) {
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE_DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE_DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   return 0;
 }
 
@@ -410,6 +443,8 @@ static int smem_setup_cfg(Handle *h) {
 // handle is created (gpb200_create), once per handle, so one process may hold handles on several GPUs.
 int gemm_smem_setup(Handle *h) {
   int rc = smem_setup_cfg<CfgBig>(h);
+  if (!rc) rc = smem_setup_cfg<CfgHalf>(h);
+  if (!rc) rc = smem_setup_cfg<CfgHalf8>(h);
   return rc ? rc : smem_setup_cfg<CfgSmall>(h);
 }
 
@@ -429,11 +464,28 @@ static int launch_cfg(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParam
   return -2;
 }
 
-// `small` selects the 16-warp zero-skipping configuration (short k-loops)
+// configuration choice: 1 Big, 2 Small (16-warp zero-skipping, short k-loops), 3 Half (two CTAs per SM)
+// Measured on B200 (profiles/bench_configs_r01.json, bench_r01*.json): configuration 4 wins or ties at every
+// size from N=512 (100.2k vs 97.0k evals/s for the zero-skipping 16-warp one) to N=4096 (455 vs 434 for
+// the one-CTA-per-SM one), so it is the default everywhere; the others stay selectable for comparison.
+static int gemm_pick_cfg(const Handle *h, int small_k) {
+  (void)small_k;
+  if (h->gemm_cfg_override) return h->gemm_cfg_override;
+  return GPB_DEFAULT_CFG;
+}
+
+// CTAs per 128x128 task of the configuration launch_gemm will pick (the trace epilogues write one
+// partial record per CTA)
+int gemm_nsplit(const Handle *h, int small_k) { return gemm_pick_cfg(h, small_k) >= 3 ? CfgHalf::NSPLIT : 1; }
+
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
   if (ntasks <= 0 || batch <= 0) return 0;
-  const bool small = h->gemm_cfg_override ? h->gemm_cfg_override == 2 : p.small_k;
-  return small ? launch_cfg<CfgSmall>(h, layout, epi, p, ntasks, batch) : launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
+  switch (gemm_pick_cfg(h, p.small_k)) {
+    case 2: return launch_cfg<CfgSmall>(h, layout, epi, p, ntasks, batch);
+    case 3: return launch_cfg<CfgHalf>(h, layout, epi, p, ntasks, batch);
+    case 4: return launch_cfg<CfgHalf8>(h, layout, epi, p, ntasks, batch);
+    default: return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
+  }
 }
 
 }  // namespace gpb

@@ -7,6 +7,7 @@
 //   nine derivative kernels         derivative_kernels.R:39-73 ; R/kernels.R:19-32 (incl. the :31 quirk)
 //   joint (y, y', y'') covariance   design_notes.Rmd:6-46 ; R/ode_gp_library.R:29-30
 #include "common.cuh"
+#include "fastexp.cuh"
 #include "gram.cuh"
 
 namespace gpb {
@@ -89,7 +90,20 @@ __global__ void __launch_bounds__(256) gram_se_batched_kernel(int n, int np, con
   const double a2 = alpha * alpha, nh = -0.5 / (rho * rho), dadd = sigma * sigma + jitter;
   double *Kb = K + b * stride;
   const int rl = 2 * (tid & 63), cq = tid >> 6;
+  if (tr != tc && r0 + TILE <= n && c0 + TILE <= n) {
+    // interior off-diagonal tile (all but O(nt) of the nt^2/2 tiles): no masks, no diagonal
+    const double x0 = xs[rl], x1 = xs[rl + 1];
+    double *dst = Kb + (r0 + rl) + (long long)(c0 + cq) * np;
 #pragma unroll 4
+    for (int s = 0; s < 32; s++) {
+      const double yc = ys[cq + 4 * s];
+      const double d0 = x0 - yc, d1 = x1 - yc;
+      *reinterpret_cast<double2 *>(dst) = make_double2(a2 * exp_nonpos(d0 * d0 * nh), a2 * exp_nonpos(d1 * d1 * nh));
+      dst += 4LL * np;
+    }
+    return;
+  }
+#pragma unroll 2
   for (int s = 0; s < 32; s++) {
     const int cl = cq + 4 * s;
     const int j = c0 + cl;
@@ -99,7 +113,7 @@ __global__ void __launch_bounds__(256) gram_se_batched_kernel(int n, int np, con
       const int i = r0 + rl + e;
       if (i < n && j < n) {
         const double d = xs[rl + e] - ys[cl];
-        v[e] = (i == j) ? a2 + dadd : a2 * exp(d * d * nh);
+        v[e] = (i == j) ? a2 + dadd : a2 * exp_nonpos(d * d * nh);
       } else {
         v[e] = (i == j) ? 1.0 : 0.0;
       }
@@ -133,7 +147,7 @@ __global__ void __launch_bounds__(256) gram_se_panel_kernel(int n, int np, const
       const int i = r0 + rl + e;
       if (i < n && j < n) {
         const double d = xs[rl + e] - ys[cl];
-        v[e] = (i == j) ? a2 + dadd : a2 * exp(d * d * nh);
+        v[e] = (i == j) ? a2 + dadd : a2 * exp_nonpos(d * d * nh);
       } else {
         v[e] = (i == j) ? 1.0 : 0.0;
       }

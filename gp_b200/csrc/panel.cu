@@ -259,8 +259,17 @@ trsm_tile_kernel(const double *Ldiag_base, double *Cbase, long long ld, long lon
   const double *Ld = Ldiag_base + (long long)item * stride + diag_off + (long long)blockIdx.x * diag_step;
   double *Ct = Cbase + (long long)item * stride + c_off + (long long)blockIdx.x * c_step;
 
-  // the C tile goes straight to registers; issue those loads first so that they overlap the staging
-  // of the diagonal tile (both are 128 KB and this kernel runs one CTA per SM)
+  // stage the diagonal tile with cp.async (column-major copy, 16B vectors): all 32 copies of a thread are
+  // in flight at once, together with the C-tile loads below (both tiles are 128 KB and this kernel runs
+  // one CTA per SM, so exposed load latency is what bounds it)
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+    const int k = idx >> 6, n2 = idx & 63;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(Ls + k * LD_L + 2 * n2);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ld + 2 * n2 + (long long)k * ld) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+
+  // the C tile goes straight to registers
   double acc[2][16][2];
   const int r0 = warp * 16;
 #pragma unroll
@@ -273,12 +282,7 @@ trsm_tile_kernel(const double *Ldiag_base, double *Cbase, long long ld, long lon
         acc[mt][nt][e] = (MODE == 0) ? Ct[r + (long long)c * ld] : ((r == c) ? 1.0 : 0.0);
       }
 
-  // stage the diagonal tile (column-major copy, 16B vectors)
-  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
-    const int k = idx >> 6, n2 = idx & 63;
-    const double2 v = *reinterpret_cast<const double2 *>(Ld + 2 * n2 + (long long)k * ld);
-    *reinterpret_cast<double2 *>(Ls + k * LD_L + 2 * n2) = v;
-  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncthreads();
   if (tid < TILE) invd[tid] = 1.0 / Ls[tid * LD_L + tid];
   __syncthreads();
