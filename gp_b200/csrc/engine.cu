@@ -109,9 +109,11 @@ int build_nodes(int lo, int hi, std::vector<Node> &nodes) {
   return lvl;
 }
 
-// in-place recursive inverse of the lower-triangular factor: per node
-//   S   = W22 * L21          (scratch buffer)        S[i,j] = sum_{k=mid..i} W[i,k] L[k,j]
-//   W21 = -S * W11           (over L21 in place)     W[i,j] = -sum_{k=j..mid-1} S[i,k] W[k,j]
+// in-place recursive inverse of the lower-triangular factor: per node (lo, mid, hi)
+//   S^T = L21^T * W22^T      (scratch buffer, UPPER tiles)   S^T[j,i] = sum_{k=mid..i} L[k,j] W[i,k]
+//   W21 = -S * W11           (over L21 in place)             W[i,j]  = -sum_{k=j..mid-1} S^T[k,i] W[k,j]
+// S is kept transposed so that in BOTH products the triangular diagonal tile (W22[i,i], W11[j,j]) is the
+// B operand of the tile GEMM, whose zero half the column-split configurations skip for a whole CTA.
 int tasks_trtri(Handle *h, int nt, TaskList *s_out, TaskList *w_out) {
   const long long ks = tkey(TK_TRTRI_S, nt), kw = tkey(TK_TRTRI_W, nt);
   if (cached(h, ks, s_out) && cached(h, kw, w_out)) return 0;
@@ -125,8 +127,10 @@ int tasks_trtri(Handle *h, int nt, TaskList *s_out, TaskList *w_out) {
       if (nd.level != lvl) continue;
       for (int i = nd.mid; i < nd.hi; i++)
         for (int j = nd.lo; j < nd.mid; j++) {
-          ts.push_back({i * TILE, nd.mid * TILE, nd.mid * TILE, j * TILE, i * TILE, j * TILE, (i - nd.mid + 1) * TILE, TF_A_TRI_LAST});
-          tw.push_back({i * TILE, j * TILE, j * TILE, j * TILE, i * TILE, j * TILE, (nd.mid - j) * TILE, TF_B_TRI_FIRST});
+          // LAYOUT_TT: A = L (k down the rows from mid, columns of tile j), B = W (rows of tile i, k along the columns)
+          ts.push_back({nd.mid * TILE, j * TILE, i * TILE, nd.mid * TILE, j * TILE, i * TILE, (i - nd.mid + 1) * TILE, TF_B_TRI_LAST});
+          // LAYOUT_TN: A = S^T (k down the rows from tile j, columns of tile i), B = W11 (k down the rows, columns of tile j)
+          tw.push_back({j * TILE, i * TILE, j * TILE, j * TILE, i * TILE, j * TILE, (nd.mid - j) * TILE, TF_B_TRI_FIRST});
         }
     }
     sort_desc(ts, fs);
@@ -221,7 +225,7 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
     p.alpha = 1.0;
     p.beta = 0.0;
     p.tasks = ts.at(lvl);
-    rc = launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, ts.count(lvl), batch);
+    rc = launch_gemm(h, LAYOUT_TT, EPI_AXPBY, p, ts.count(lvl), batch);
     if (rc) return rc;
     GemmParams q{};
     q.small_k = gemm_small_k(np);
@@ -231,7 +235,7 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
     q.alpha = -1.0;
     q.beta = 0.0;
     q.tasks = tw.at(lvl);
-    rc = launch_gemm(h, LAYOUT_NN, EPI_AXPBY, q, tw.count(lvl), batch);
+    rc = launch_gemm(h, LAYOUT_TN, EPI_AXPBY, q, tw.count(lvl), batch);
     if (rc) return rc;
   }
   return 0;

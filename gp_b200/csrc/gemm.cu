@@ -434,6 +434,7 @@ static int smem_setup_cfg(Handle *h) {
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE_DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   return 0;
@@ -455,6 +456,7 @@ static int launch_cfg(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParam
       case LAYOUT_NT: return launch_one<Cfg, false, false, EPI_AXPBY>(h, p, ntasks, batch);
       case LAYOUT_TN: return launch_one<Cfg, true, true, EPI_AXPBY>(h, p, ntasks, batch);
       case LAYOUT_NN: return launch_one<Cfg, false, true, EPI_AXPBY>(h, p, ntasks, batch);
+      case LAYOUT_TT: return launch_one<Cfg, true, false, EPI_AXPBY>(h, p, ntasks, batch);
     }
   } else if (layout == LAYOUT_TN) {
     if (epi == EPI_TRACE_DERIV) return launch_one<Cfg, true, true, EPI_TRACE_DERIV>(h, p, ntasks, batch);

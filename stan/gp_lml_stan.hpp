@@ -16,6 +16,7 @@
 // device the reference uses in cubic_interpolated_gp.hpp:28 (precomp_v_vari).
 // A non-positive-definite matrix throws std::domain_error, as Stan Math's cholesky_decompose does,
 // so NUTS rejects the proposal.
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -73,5 +74,52 @@ inline double gp_lml(const std::vector<double>& x, const Eigen::Matrix<double, E
                      const double& alpha, const double& rho, const double& sigma, std::ostream* pstream__) {
   double lml;
   gpb200_stan::eval(x, y, alpha, rho, sigma, lml, nullptr);
+  return lml;
+}
+
+// ---- GP observed through first derivatives only: the model block of the Stan program embedded in
+// gpderivs.py:62-83 (Sigma = sf2 * covdd(t_i, t_j, l2) + s2 I; dx ~ multi_normal(zeros, Sigma)) as one
+// call, in that program's own (sf2, l2, s2) parametrisation:
+//
+//   functions { real gp_lml_dd(vector t, vector dx, real sf2, real l2, real s2); }
+//   model     { target += gp_lml_dd(t, dx, sf2, l2, s2); ... cauchy priors ... }
+namespace gpb200_stan {
+inline void eval_dd(const Eigen::VectorXd& t, const Eigen::VectorXd& dx, double sf2, double l2, double s2, double& lml,
+                    double* grad3) {
+  const double alpha = std::sqrt(sf2), l = std::sqrt(0.5 * l2), sigma = std::sqrt(s2);
+  const double theta[3] = {alpha, l, sigma};
+  double g[3];
+  int info = 0;
+  const int rc = gpb200_lml_grad_deriv_batched(handle(), (int)t.size(), /*order0=*/1, /*nblocks=*/1, 1, t.data(), 0,
+                                               dx.data(), 0, theta, 0.0, grad3 != nullptr, &lml, g, &info);
+  if (rc < 0) throw std::runtime_error(std::string("gp_lml_dd: ") + gpb200_last_error(handle()));
+  if (info > 0) throw std::domain_error("gp_lml_dd: covariance is not positive definite (pivot " + std::to_string(info) + ")");
+  if (grad3) {  // chain rule to (sf2, l2, s2)
+    grad3[0] = g[0] / (2.0 * alpha);
+    grad3[1] = g[1] / (4.0 * l);
+    grad3[2] = g[2] / (2.0 * sigma);
+  }
+}
+}  // namespace gpb200_stan
+
+template <typename T0__, typename T1__, typename T2__>
+typename boost::math::tools::promote_args<T0__, T1__, T2__>::type
+gp_lml_dd(const Eigen::Matrix<double, Eigen::Dynamic, 1>& t, const Eigen::Matrix<double, Eigen::Dynamic, 1>& dx,
+          const T0__& sf2, const T1__& l2, const T2__& s2, std::ostream* pstream__) {
+  using stan::math::value_of;
+  double lml, g[3];
+  gpb200_stan::eval_dd(t, dx, value_of(sf2), value_of(l2), value_of(s2), lml, g);
+  std::vector<stan::math::var> operands;
+  std::vector<double> partials;
+  gpb200_stan::add_operand(operands, partials, sf2, g[0]);
+  gpb200_stan::add_operand(operands, partials, l2, g[1]);
+  gpb200_stan::add_operand(operands, partials, s2, g[2]);
+  return stan::math::precomputed_gradients(lml, operands, partials);
+}
+
+inline double gp_lml_dd(const Eigen::Matrix<double, Eigen::Dynamic, 1>& t, const Eigen::Matrix<double, Eigen::Dynamic, 1>& dx,
+                        const double& sf2, const double& l2, const double& s2, std::ostream* pstream__) {
+  double lml;
+  gpb200_stan::eval_dd(t, dx, sf2, l2, s2, lml, nullptr);
   return lml;
 }

@@ -5,3 +5,6 @@ using stan::math::var;
 var f1(const std::vector<double> &x, const Eigen::VectorXd &y, var a, var r, var s) { return gp_lml(x, y, a, r, s, nullptr); }
 var f2(const std::vector<double> &x, const Eigen::VectorXd &y, double a, var r, double s) { return gp_lml(x, y, a, r, s, nullptr); }
 double f3(const std::vector<double> &x, const Eigen::VectorXd &y) { return gp_lml(x, y, 1.0, 1.0, 0.3, nullptr); }
+var f4(const Eigen::VectorXd &t, const Eigen::VectorXd &dx, var a, var l2, var s2) { return gp_lml_dd(t, dx, a, l2, s2, nullptr); }
+var f5(const Eigen::VectorXd &t, const Eigen::VectorXd &dx, var a, double l2, var s2) { return gp_lml_dd(t, dx, a, l2, s2, nullptr); }
+double f6(const Eigen::VectorXd &t, const Eigen::VectorXd &dx) { return gp_lml_dd(t, dx, 1.0, 2.0, 0.04, nullptr); }

@@ -14,3 +14,9 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_tile_kernel
     -o gpurun_out/prof_gemm_lauum_$TAG -f $CMD > gpurun_out/ncu_lauum_$TAG.log 2>&1
 ls -la gpurun_out/
 tail -2 gpurun_out/plain_$TAG.log
+$CMD > gpurun_out/plain4_$TAG.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gram_se_batched -c 1 \
+    -o gpurun_out/prof_gram_$TAG -f $CMD > gpurun_out/ncu_gram_$TAG.log 2>&1
+$CMD > gpurun_out/plain5_$TAG.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gemm_tile_kernel -s 184 -c 1 \
+    -o gpurun_out/prof_gemm_trtri_$TAG -f $CMD > gpurun_out/ncu_trtri_$TAG.log 2>&1
