@@ -41,6 +41,38 @@ def run(h, stream, dev, n, B, per_item_xy, reps=3):
             "tflops": round(B * float(n) ** 3 / ms * 1e-9, 2), "classes_ms": {k: round(v[0] / reps, 3) for k, v in prof.items()}}
 
 
+def run_deriv(h, stream, dev, n, nblocks, B, reps=3):
+    """C2: joint (y, y', y'') covariance, N = nblocks * n, B theta draws on one grid (device-resident)."""
+    rng = np.random.default_rng(2)
+    t = np.linspace(0, 10, n)
+    y = np.concatenate([np.sin(t), np.cos(t), -np.sin(t)][:nblocks]) + 0.2 * rng.standard_normal(n * nblocks)
+    th = np.column_stack([rng.uniform(0.7, 1.5, B), rng.uniform(0.8, 1.6, B)] + [rng.uniform(0.1, 0.4, B) for _ in range(nblocks)])
+    dt = torch.from_numpy(t).to(dev); dy = torch.from_numpy(y).to(dev); dth = torch.from_numpy(th).to(dev)
+    lml = torch.empty(B, dtype=torch.float64, device=dev); grad = torch.empty(B, 2 + nblocks, dtype=torch.float64, device=dev)
+    info = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def call():
+        rc = h.lib.gpb200_lml_grad_deriv_batched(h._h, n, 0, nblocks, B, dt.data_ptr(), 0, dy.data_ptr(), 0, dth.data_ptr(), 1e-6, 1,
+                                                 lml.data_ptr(), grad.data_ptr(), info.data_ptr())
+        assert rc == 0, rc
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize()
+    h.set_profiling(True)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        call()
+    e1.record(stream); torch.cuda.synchronize()
+    prof = h.get_profile(); h.set_profiling(False)
+    ms = e0.elapsed_time(e1) / reps
+    assert int(info.abs().sum().item()) == 0
+    N = n * nblocks
+    return {"config": "C2 joint derivative covariance", "n_grid": n, "nblocks": nblocks, "N": N, "B": B, "ms_per_batch": round(ms, 3),
+            "evals_per_s": round(B / ms * 1e3, 1), "tflops": round(B * float(N) ** 3 / ms * 1e-9, 2),
+            "classes_ms": {k: round(v[0] / reps, 3) for k, v in prof.items()}}
+
+
 def main():
     dev = torch.device("cuda", 0)
     h = capi.Handle(0)
@@ -50,6 +82,8 @@ def main():
     for n, B, per in [(2048, 512, False), (1024, 256, True), (1024, 32, True), (512, 1024, False), (100, 4096, False), (100, 1, False)]:
         r = run(h, stream, dev, n, B, per)
         out.append(r); print(json.dumps(r), flush=True)
+    r = run_deriv(h, stream, dev, 512, 3, 256)
+    out.append(r); print(json.dumps(r), flush=True)
     json.dump(out, open("gpurun_out/bench_configs.json", "w"), indent=1)
 
 
