@@ -80,50 +80,59 @@ __global__ void __launch_bounds__(256) trmv_lower_t_kernel(int np, const double 
 // s = rhs_j - L[j, 0:j] z[0:j] (two k-halves per row), then z_j = Wdiag_j s with the pre-inverted
 // diagonal tile.  z lives in global memory (written and re-read by this CTA only, ordered by the
 // block barriers), so any n fits.
-__global__ void __launch_bounds__(256) trsv_blocked_kernel(int np, const double *__restrict__ L,
+constexpr int TRSV_KSPLIT = 8;  // k-groups per row: 1024 threads per item keep enough loads in flight to approach HBM speed
+__global__ void __launch_bounds__(TILE * TRSV_KSPLIT) trsv_blocked_kernel(int np, const double *__restrict__ L,
                                                           const double *__restrict__ Wdiag, long long stride,
                                                           const double *__restrict__ y, long long y_stride,
                                                           const double *__restrict__ mu, int n_valid,
                                                           double *z, long long z_stride) {
-  __shared__ double part[TILE];
+  constexpr int KS = TRSV_KSPLIT;
+  __shared__ double part[KS][TILE];
   __shared__ double sv[TILE];
   const long long b = blockIdx.x;
   const double *Lb = L + b * stride, *Wb = Wdiag + b * stride;
   const double *yb = y + b * y_stride;
   double *zb = z + b * z_stride;
-  const int tid = threadIdx.x, r = tid & 127, half = tid >> 7;
+  const int tid = threadIdx.x, r = tid & 127, grp = tid >> 7;
   const int nt = np / TILE;
   for (int j = 0; j < nt; j++) {
     const int i = j * TILE + r;
-    const int kmax = j * TILE;
+    const int kmax = j * TILE;  // multiple of 128, so every group's strided range has the same length
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const double *lp = Lb + i + (long long)half * np;
-    for (int k = half; k < kmax; k += 8) {
+    const double *lp = Lb + i + (long long)grp * np;
+    for (int k = grp; k < kmax; k += 4 * KS) {
       s0 = fma(lp[0], zb[k], s0);
-      s1 = fma(lp[2LL * np], zb[k + 2], s1);
-      s2 = fma(lp[4LL * np], zb[k + 4], s2);
-      s3 = fma(lp[6LL * np], zb[k + 6], s3);
-      lp += 8LL * np;
+      s1 = fma(lp[(long long)KS * np], zb[k + KS], s1);
+      s2 = fma(lp[2LL * KS * np], zb[k + 2 * KS], s2);
+      s3 = fma(lp[3LL * KS * np], zb[k + 3 * KS], s3);
+      lp += 4LL * KS * np;
     }
-    const double ssum = (s0 + s1) + (s2 + s3);
-    if (half == 1) part[r] = ssum;
+    part[grp][r] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    if (half == 0) {
+    if (grp == 0) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < KS; q++) acc += part[q][r];
       double rhs = 0.0;
       if (i < n_valid) rhs = yb[i] - (mu ? mu[i] : 0.0);
-      sv[r] = rhs - (ssum + part[r]);
+      sv[r] = rhs - acc;
     }
     __syncthreads();
     // z_j = Wdiag_j * sv  (lower-triangular 128x128, strict upper is zero)
     const double *wd = Wb + (long long)j * TILE * (np + 1);
     double t0 = 0.0, t1 = 0.0;
-    for (int k = half; k < TILE; k += 4) {
+    for (int k = grp; k < TILE; k += 2 * KS) {
       t0 = fma(wd[r + (long long)k * np], sv[k], t0);
-      t1 = fma(wd[r + (long long)(k + 2) * np], sv[k + 2], t1);
+      t1 = fma(wd[r + (long long)(k + KS) * np], sv[k + KS], t1);
     }
-    if (half == 1) part[r] = t0 + t1;
+    part[grp][r] = t0 + t1;
     __syncthreads();
-    if (half == 0) zb[i] = t0 + t1 + part[r];
+    if (grp == 0) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < KS; q++) acc += part[q][r];
+      zb[i] = acc;
+    }
     __syncthreads();
   }
 }
@@ -352,7 +361,7 @@ int launch_trmv_lower_t(Handle *h, int np, const double *W, long long stride, co
 int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
                         long long y_stride, const double *mu, int n_valid, double *z, long long z_stride, int batch) {
   ProfScope ps__(h, PC_SOLVE);
-  trsv_blocked_kernel<<<batch, 256, 0, h->stream>>>(np, L, Wdiag, stride, y, y_stride, mu, n_valid, z, z_stride);
+  trsv_blocked_kernel<<<batch, TILE * TRSV_KSPLIT, 0, h->stream>>>(np, L, Wdiag, stride, y, y_stride, mu, n_valid, z, z_stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
