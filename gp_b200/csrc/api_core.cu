@@ -30,6 +30,8 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
       cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return -1000; }
   const char *gc = getenv("GPB200_GEMM_CFG");  // tuning knob, same meaning as gpb200_set_gemm_config
   if (gc && gc[0] >= '0' && gc[0] <= '4') h->gemm_cfg_override = gc[0] - '0';
+  const char *tp = getenv("GPB200_TRSM_PIPELINED");
+  if (tp && tp[0] == '0') h->trsm_pipelined = 0;
   const char *ng = getenv("GPB200_NO_GRAPH");
   if (ng && ng[0] == '1') h->graphs_enabled = 0;
   *out = h;

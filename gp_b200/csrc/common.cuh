@@ -63,6 +63,7 @@ struct Handle {
   long long ws_limit = 0;
   int chol_panel_override = 0;
   int gemm_cfg_override = 0;  // 0 auto, 1 force Big (8 warps, 1 CTA/SM), 2 Small (16 warps, zero-skipping), 3 Half (128x64, 2 CTAs/SM)
+  int trsm_pipelined = 1;     // 0: one tile per CTA (the first TRSM tile kernel); env GPB200_TRSM_PIPELINED
   char err[512] = {0};
   // grow-only device workspace
   void *ws = nullptr;

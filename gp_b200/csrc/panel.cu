@@ -352,7 +352,147 @@ trsm_tile_kernel(const double *Ldiag_base, double *Cbase, long long ld, long lon
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pipelined TRSM over several row tiles of one block column (MODE 0 semantics).  Timing the kernel above
+// with its arithmetic removed showed 7.5 of its 18.1 ms per N=4096 step are exposed global-memory time
+// (one CTA per SM: load 256 KB, compute, store 128 KB, nothing overlaps).  Here one CTA keeps the diagonal
+// tile in shared memory for up to `tiles_per_cta` row tiles -- packed (only the lower triangle, in groups of
+// 8 columns: 72 KB instead of 135 KB) so that a full 128x128 prefetch buffer fits next to it -- and the
+// cp.async prefetch of the next C tile runs under the substitution + DMMA work of the current one.
+// The arithmetic per element is that of trsm_tile_kernel<0>.  What is left (14.4 of 17.3 ms with loads and stores
+// removed) is the substitution chain itself: its DMUL/DFMA steps queue behind the other warps' DMMAs on the one
+// FP64 pipe (ncu: 44.6 % DMMA-active, DFMA stalls 70 % short-scoreboard + 23 % math-pipe); 16 warps of 8 rows
+// instead of 8 warps of 16 rows measured the same.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int lpk_ld(int cb) { return TILE + 4 - 8 * cb; }   // rows 8cb..127 (+4 pad): == 4 or 12 mod 16
+__host__ __device__ constexpr int lpk_off(int cb) { return 8 * (cb * (TILE + 4) - 4 * cb * (cb - 1)); }  // sum_{c<cb} 8*lpk_ld(c)
+constexpr int LPK_DOUBLES = lpk_off(16);          // 9216
+constexpr int LD_CB = TILE + 2;                   // prefetch buffer: column-major, 130 (conflict-free 8-byte reads)
+constexpr int TRSM_PIPE_SMEM_BYTES = (LPK_DOUBLES + TILE + TILE * LD_CB) * (int)sizeof(double);
+
+template <int MT>  // m8 row tiles per warp: 128 / (8 MT) warps per CTA
+__global__ void __launch_bounds__(32 * (16 / MT), 1)
+trsm_tiles_pipelined_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long stride, long long diag_off,
+                            long long c_off, int ntiles, int tiles_per_cta) {
+  extern __shared__ __align__(16) double sm[];
+  double *Lp = sm;                      // packed: Lp[lpk_off(cb) + kk*lpk_ld(cb) + (n - 8cb)] = L[n][8cb + kk], n >= 8cb
+  double *invd = sm + LPK_DOUBLES;      // 1 / L[n][n]
+  double *Cb = invd + TILE;             // Cb[c*LD_CB + r] = C[r][c] of the tile being fetched
+  constexpr int NTH = 32 * (16 / MT);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int item = blockIdx.y;
+  const double *Ld = Ldiag_base + (long long)item * stride + diag_off;
+  const int t0 = blockIdx.x * tiles_per_cta;
+  const int t1 = min(ntiles, t0 + tiles_per_cta);
+  double *Ct = Cbase + (long long)item * stride + c_off + (long long)t0 * TILE;
+
+  auto cp16 = [](double *dst, const double *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+  };
+  auto prefetch_c = [&](const double *src) {
+#pragma unroll 8
+    for (int idx = tid; idx < TILE * TILE / 2; idx += NTH) {
+      const int c = idx >> 6, r2 = idx & 63;
+      cp16(Cb + c * LD_CB + 2 * r2, src + 2 * r2 + (long long)c * ld);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  // diagonal tile, packed by groups of 8 columns
+#pragma unroll
+  for (int cb = 0; cb < 16; cb++) {
+    const int rows2 = (TILE - 8 * cb) / 2;          // 16-byte chunks per column of this group
+    for (int idx = tid; idx < 8 * rows2; idx += NTH) {
+      const int kk = idx / rows2, r2 = idx - kk * rows2;
+      cp16(Lp + lpk_off(cb) + kk * lpk_ld(cb) + 2 * r2, Ld + (8 * cb + 2 * r2) + (long long)(8 * cb + kk) * ld);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  prefetch_c(Ct);
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  if (tid < TILE) invd[tid] = 1.0 / Lp[lpk_off(tid >> 3) + (tid & 7) * lpk_ld(tid >> 3) + (tid & 7)];
+  __syncthreads();
+
+  const unsigned FULL = 0xffffffffu;
+  const int qbase = lane & ~3;
+  const int r0 = warp * 8 * MT;
+  for (int ti = t0; ti < t1; ti++) {
+    double acc[MT][16][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 16; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) acc[mt][nt][e] = Cb[(nt * 8 + 2 * t + e) * LD_CB + r0 + mt * 8 + g];
+    __syncthreads();  // everybody has taken its rows out of the buffer
+    if (ti + 1 < t1) prefetch_c(Ct + TILE);  // next row tile, in flight during the arithmetic below
+
+#pragma unroll
+    for (int cb = 0; cb < 16; cb++) {
+      const double *Lg = Lp + lpk_off(cb);  // group cb: Lg[kk*ld + (n - 8cb)]
+      const int ldg = lpk_ld(cb);
+      // (i) substitution inside the 8x8 diagonal block; a row's 8 values live in one quad
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const int owner = qbase + (c >> 1);
+        const double dinv = invd[cb * 8 + c];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+          double xv = acc[mt][cb][c & 1] * dinv;
+          if (t == (c >> 1)) acc[mt][cb][c & 1] = xv;
+          xv = __shfl_sync(FULL, xv, owner);
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int cp = 2 * t + e;
+            if (cp > c) acc[mt][cb][e] = fma(-xv, Lg[c * ldg + cp], acc[mt][cb][e]);
+          }
+        }
+      }
+      // (ii) re-layout the solved 8 columns from accumulator layout to mma A-operand layout
+      double af[MT][2];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          const int src = qbase + 2 * ks + (t >> 1);
+          const double v0 = __shfl_sync(FULL, acc[mt][cb][0], src);
+          const double v1 = __shfl_sync(FULL, acc[mt][cb][1], src);
+          af[mt][ks] = (t & 1) ? v1 : v0;
+        }
+      // (iii) rank-8 update of the columns to the right:  C[:, n] -= X[:, cb] * L[n, cb]^T
+      // (k-step outermost: the two DMMAs that accumulate into the same tile are a whole sweep apart)
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+#pragma unroll
+        for (int nt = 0; nt < 16; nt++) {
+          if (nt > cb) {
+            const double bfv = -Lg[(ks * 4 + t) * ldg + (nt - cb) * 8 + g];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) dmma884p(acc[mt][nt], af[mt][ks], bfv);
+          }
+        }
+      }
+    }
+
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 16; nt++) {
+        const int r = r0 + mt * 8 + g, c = nt * 8 + 2 * t;
+        Ct[r + (long long)c * ld] = acc[mt][nt][0];
+        Ct[r + (long long)(c + 1) * ld] = acc[mt][nt][1];
+      }
+    Ct += TILE;
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();  // the next tile has landed for everybody
+  }
+}
+
 int panel_smem_setup(Handle *h) {
+  GPB_CUDA(h, cudaFuncSetAttribute(trsm_tiles_pipelined_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_PIPE_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
   return 0;
@@ -375,9 +515,18 @@ int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int 
 int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, long long c_off,
                          int ntiles, int batch) {
   if (ntiles <= 0) return 0;
-  dim3 grid(ntiles, batch);
+  // tiles per CTA: as many as still leave every SM several CTAs (the diagonal tile is staged once per CTA and
+  // the next tile's loads hide under the current tile's arithmetic)
+  const long long total = (long long)ntiles * batch;
+  const int tpc = total >= 148 * 16 ? 4 : (total >= 148 * 6 ? 2 : 1);
   ProfScope ps__(h, PC_TRSM);
-  trsm_tile_kernel<0><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, 0, c_off, TILE);
+  if (tpc == 1 || h->trsm_pipelined == 0) {
+    dim3 grid(ntiles, batch);
+    trsm_tile_kernel<0><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, 0, c_off, TILE);
+  } else {
+    dim3 grid((ntiles + tpc - 1) / tpc, batch);
+    trsm_tiles_pipelined_kernel<2><<<grid, 256, TRSM_PIPE_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off, ntiles, tpc);
+  }
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
