@@ -1,12 +1,11 @@
 // Batched FP64 tensor-core (DMMA) tile GEMM for sm_100a.
 //
-// One CTA computes one 128x128 output tile of one matrix of the batch from a task list
-// (blockIdx.x = task, blockIdx.y = batch item).  The contraction streams 16-wide k-chunks of both
-// operands through a 4-stage cp.async (LDGSTS) pipeline into padded shared memory; fragments are
-// read conflict-free (leading dimensions == 4 mod 16 doubles) and fed to
+// One CTA (or a pair of column-half CTAs) computes one 128x128 output tile of one matrix of the batch
+// from a task list (blockIdx.x = task * NSPLIT + half, blockIdx.y = batch item).  The contraction
+// streams 16-wide k-chunks of both operands through a cp.async (LDGSTS) pipeline into padded shared
+// memory; fragments are read conflict-free (leading dimensions == 4 mod 16 doubles) and fed to
 // mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- tcgen05 has no FP64 kind, so this IS the FP64
 // tensor path on B200; measured peak 37.0 TFLOP/s, profiles/fp64_peak_r01.json).
-// 8 warps, warp tile 64(m) x 32(n): 32 DMMAs per 12 shared-memory fragment loads.
 //
 // The mma is used "transposed" (mma rows <-> n, mma cols <-> m) so that each thread's two
 // accumulator values are adjacent in the column-major output: 16-byte global accesses.
@@ -14,9 +13,11 @@
 // This kernel carries every O(N^3) stage of the path:
 //   NT  C = C0 - A B^T          left-looking Cholesky block-column update (replaces the inside of
 //                               Eigen LLT under cholesky_decompose, fit_hyperparameters.stan:25)
-//   NN  T = L21 W11, W21 = -W22 T   recursive triangular inverse (K^-1 for the gradient)
+//   TT  S^T = L21^T W22^T  and  TN  W21 = -S W11     recursive triangular inverse (K^-1 for the gradient)
 //   TN  G = W^T W  + fused trace epilogue  0.5 tr((a a^T - K^-1) dK/dtheta)  (the reverse sweep
-//                               of multi_normal_cholesky -> cholesky_decompose -> cov_exp_quad)
+//                               of multi_normal_cholesky -> cholesky_decompose -> cov_exp_quad), for the
+//                               SE kernel and for the joint derivative-observation kernels
+//   NN                          products of the forward-mode tangent and of mvrnorm
 #include "common.cuh"
 #include "fastexp.cuh"
 
