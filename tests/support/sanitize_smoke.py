@@ -1,5 +1,5 @@
 """Small end-to-end pass over every C-ABI entry point for compute-sanitizer (memcheck):
-  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+  compute-sanitizer --tool memcheck python tests/support/sanitize_smoke.py
 Sizes are tiny on purpose (sanitizer slows kernels ~100x)."""
 import sys
 
