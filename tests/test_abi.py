@@ -63,6 +63,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU oracle", ""), os.path.join(dirpath, f)
+    # the measurement/profiling tools, the examples and the R / Stan bindings do not touch it either
+    for sub in ("tools", "examples", "r", "stan"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".sh", ".c", ".hpp", ".R", ".cu")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dirpath, f)
 
 
 def test_r_shim_type_checks_against_mock_r_api():
