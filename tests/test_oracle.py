@@ -228,3 +228,26 @@ def test_philox_known_answer_and_normal_moments():
     assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3.0) < 0.06
     assert np.array_equal(philox.normals(42, 100, offset=1000), philox.normals(42, 1100)[1000:])
     assert not np.array_equal(philox.normals(43, 100), z[:100])
+
+
+# ---- independent third-party corroboration of the "parity unpinned" rows (a4-a7) ---------------------
+def test_lml_and_gradient_agree_with_scikit_learn_gpr():
+    """The reference pins no output for the Stan-Math rows and Stan Math cannot run here, so besides
+    NumPy <-> C <-> mpmath <-> finite differences the oracle is checked against an independent,
+    widely used implementation of the same quantity: scikit-learn's GaussianProcessRegressor
+    (ConstantKernel * RBF + WhiteKernel = alpha^2 exp(-d^2 / 2 rho^2) + sigma^2 I), whose
+    log_marginal_likelihood(theta, eval_gradient=True) works in log-parameters."""
+    pytest.importorskip("sklearn")
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, WhiteKernel
+    for n, (a, r, s) in ((100, (1.0, 1.0, 0.2)), (257, (1.3, 0.8, 0.25)), (400, (0.6, 2.1, 0.45))):
+        x, y = o.synth_xy(n, 3)
+        k = ConstantKernel(a * a) * RBF(r) + WhiteKernel(s * s)
+        g = GaussianProcessRegressor(k, alpha=0.0, optimizer=None).fit(x[:, None], y)
+        v, gr = g.log_marginal_likelihood(np.log([a * a, r, s * s]), eval_gradient=True)
+        rv, rg = o.lml_grad(x, y, a, r, s)
+        assert abs(v - rv) <= 1e-11 * abs(rv)
+        chain = np.array([rg[0] * a / 2.0, rg[1] * r, rg[2] * s / 2.0])   # d/dlog(alpha^2), d/dlog(rho), d/dlog(sigma^2)
+        assert np.max(np.abs(gr - chain)) <= 1e-9 * np.max(np.abs(chain))
+        rv2, rg2 = o.lml_grad_lapack(x, y, a, r, s)
+        assert abs(v - rv2) <= 1e-11 * abs(rv2) and np.max(np.abs(rg2 - rg)) <= 1e-9 * np.max(np.abs(rg))
