@@ -29,7 +29,7 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
       cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return -1000; }
   const char *gc = getenv("GPB200_GEMM_CFG");  // tuning knob, same meaning as gpb200_set_gemm_config
-  if (gc && gc[0] >= '0' && gc[0] <= '4') h->gemm_cfg_override = gc[0] - '0';
+  if (gc && gc[0] >= '0' && gc[0] <= '2') h->gemm_cfg_override = gc[0] - '0';
   const char *tp = getenv("GPB200_TRSM_PIPELINED");
   if (tp && tp[0] == '0') h->trsm_pipelined = 0;
   const char *ng = getenv("GPB200_NO_GRAPH");
@@ -82,9 +82,9 @@ extern "C" int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles) {
   return 0;
 }
 
-// test/tuning knob: 0 automatic, 1 force the 8-warp GEMM configuration, 2 force the 16-warp zero-skipping one
+// test/tuning knob: 0 default, 1 one 128x128 CTA per SM, 2 two 128x64 half-tile CTAs per SM
 extern "C" int gpb200_set_gemm_config(gpb200_handle_t h, int cfg) {
-  if (!h || cfg < 0 || cfg > 4) return -1;
+  if (!h || cfg < 0 || cfg > 2) return -1;
   h->gemm_cfg_override = cfg;
   return 0;
 }
@@ -337,7 +337,6 @@ int solve_common(Handle *h, int n, int nrhs, const double *L, int ldl, double *B
   TaskList t1;
   RC(tasks_mul(h, TK_MUL_WB, nt, rt, &t1));
   GemmParams p{};
-  p.small_k = gemm_small_k(np);
   p.A = mref(Lbuf, np, 0);
   p.B = mref(B0, np, 0);
   p.C = mref(B1, np, 0);
@@ -349,7 +348,6 @@ int solve_common(Handle *h, int n, int nrhs, const double *L, int ldl, double *B
     TaskList t2;
     RC(tasks_mul(h, TK_MUL_WTB, nt, rt, &t2));
     GemmParams q{};
-    q.small_k = gemm_small_k(np);
     q.A = mref(Lbuf, np, 0);
     q.B = mref(B1, np, 0);
     q.C = mref(B0, np, 0);

@@ -73,7 +73,6 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
         RC(launch_trmv_lower_n(h, np, Lbuf, mat, cy, ys, n, zbuf, np, bc));
         RC(launch_trmv_lower_t(h, np, Lbuf, mat, zbuf, np, abuf, np, bc));
         GemmParams p{};
-        p.small_k = gemm_small_k(np);
         p.A = mref(Lbuf, np, mat);
         p.B = mref(Lbuf, np, mat);
         p.C = mref(nullptr, np, mat);
@@ -92,10 +91,10 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
         else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
       }
       if (sp.deriv)
-        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, gemm_small_k(np)), cth, dlml + b0,
+        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h), cth, dlml + b0,
                                  dgrad + (long long)b0 * ts, bc));
       else
-        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, gemm_small_k(np)), cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
+        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h), cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
     }
     return 0;
   };
@@ -262,20 +261,17 @@ int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, const 
   RC(tasks_tangent(h, nt, &t1, &ta, &tl));
   {  // T1 = W Kdot  -> Sbuf (lower tiles)
     GemmParams p{};
-    p.small_k = gemm_small_k(np);
     p.A = mref(Lbuf, np, st); p.B = mref(Dbuf, np, st); p.C = mref(Sbuf, np, st); p.alpha = 1.0; p.tasks = t1.at(0);
     RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, t1.count(0), P));
   }
   {  // A = T1 W^T -> Dbuf (lower tiles)
     GemmParams p{};
-    p.small_k = gemm_small_k(np);
     p.A = mref(Sbuf, np, st); p.B = mref(Lbuf, np, st); p.C = mref(Dbuf, np, st); p.alpha = 1.0; p.tasks = ta.at(0);
     RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, ta.count(0), P));
   }
   RC(launch_phi_lower(h, np, Dbuf, st, P));
   {  // Ldot = L Phi(A) -> Sbuf (lower tiles)
     GemmParams p{};
-    p.small_k = gemm_small_k(np);
     p.A = mref(Lkeep, np, st); p.B = mref(Dbuf, np, st); p.C = mref(Sbuf, np, st); p.alpha = 1.0; p.tasks = tl.at(0);
     RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, tl.count(0), P));
   }
@@ -429,13 +425,11 @@ int condition_device(Handle *h, Arena &a, int n, int m, const double *K, long lo
   RC(tasks_cond(h, np / TILE, mp / TILE, &tv, &tc));
   {
     GemmParams p{};
-    p.small_k = gemm_small_k(np);
     p.A = mref(Lbuf, np, 0); p.B = mref(Ksp, mp, 0); p.C = mref(V, np, 0); p.alpha = 1.0; p.tasks = tv.at(0);
     RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tv.count(0), 1));
   }
   {
     GemmParams p{};
-    p.small_k = gemm_small_k(np);
     p.A = mref(V, np, 0); p.B = mref(V, np, 0); p.C = mref(Cp, mp, 0); p.C0 = mref(Cp, mp, 0);
     p.alpha = -1.0; p.beta = 1.0; p.tasks = tc.at(0);
     RC(launch_gemm(h, LAYOUT_TN, EPI_AXPBY, p, tc.count(0), 1));

@@ -54,7 +54,6 @@ extern "C" int gpb200_mg_panel_factor(gpb200_handle_t h, int n, int col0, int nc
     RC(upload_tasks(h, key, t, off, &tl));
   }
   GemmParams p{};
-  p.small_k = gemm_small_k(np);
   p.A = mref(P, ldp, 0);
   p.B = mref(P, ldp, 0);
   p.C = mref(P, ldp, 0);
@@ -92,7 +91,6 @@ extern "C" int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int p
     RC(upload_tasks(h, key, t, off, &tl));
   }
   GemmParams p{};
-  p.small_k = gemm_small_k(np);
   p.A = mref(const_cast<double *>(P), ldp, 0);
   p.B = mref(const_cast<double *>(P), ldp, 0);
   p.C = mref(Cp, ldc, 0);

@@ -74,7 +74,6 @@ extern "C" int gpb200_mvrnorm(gpb200_handle_t h, int ndraws, int m, const double
   TaskList tl;
   RC(tasks_lz(h, mp / TILE, dp / TILE, &tl));
   GemmParams p{};
-  p.small_k = gemm_small_k(mp);
   p.A = mref(Lbuf, mp, 0); p.B = mref(Z, mp, 0); p.C = mref(X, mp, 0); p.alpha = 1.0; p.tasks = tl.at(0);
   RC(launch_gemm(h, LAYOUT_NN, EPI_AXPBY, p, tl.count(0), 1));
   RC(launch_add_mean_transpose(h, m, ndraws, X, mp, dmu, dout, ldout));

@@ -24,8 +24,8 @@ struct TileTask {
   int flags;     // TF_* bits
 };
 // task flags: bit0 = diagonal tile of a symmetric result (trace epilogue weight 1 instead of 2); the
-// others mark a triangular operand tile at the first / last 128 of the k-range, so that warps whose
-// sub-tile only meets its zero half skip those chunks
+// others mark a triangular operand tile at the first / last 128 of the k-range: a column-half CTA that
+// only meets the zero half of a triangular B tile contracts over 64 fewer k (the A flags are descriptive)
 enum { TF_DIAG = 1,
        TF_A_TRI_FIRST = 2,   // first k-tile of A is zero where k_local < m_local
        TF_A_TRI_LAST = 4,    // last  k-tile of A is zero where k_local > m_local
@@ -52,7 +52,6 @@ struct GemmParams {
   // derivative-observation trace epilogue (EPI_TRACE_DERIV): the matrix is nblocks x nblocks blocks of
   // n_grid x n_grid; block b carries derivative order order0 + b; theta is B x theta_stride
   int n_grid, order0, theta_stride;
-  int small_k;                               // 1: short k-loops -> 16-warp zero-skipping GEMM configuration
 };
 
 struct Handle {
@@ -62,7 +61,7 @@ struct Handle {
   long long launches = 0;
   long long ws_limit = 0;
   int chol_panel_override = 0;
-  int gemm_cfg_override = 0;  // 0 auto, 1 force Big (8 warps, 1 CTA/SM), 2 Small (16 warps, zero-skipping), 3 Half (128x64, 2 CTAs/SM)
+  int gemm_cfg_override = 0;  // 0 default (2), 1 one 128x128 CTA per SM, 2 two 128x64 half-tile CTAs per SM
   int trsm_pipelined = 1;     // 0: one tile per CTA (the first TRSM tile kernel); env GPB200_TRSM_PIPELINED
   char err[512] = {0};
   // grow-only device workspace
@@ -144,7 +143,7 @@ enum GemmEpi { EPI_AXPBY = 0, EPI_TRACE = 1, EPI_TRACE_DERIV = 2 };
 
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch);
 int gemm_smem_setup(Handle *h);
-int gemm_nsplit(const Handle *h, int small_k);
+int gemm_nsplit(const Handle *h);
 
 // panel kernels (panel.cu)
 int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n,

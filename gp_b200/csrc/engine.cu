@@ -179,7 +179,6 @@ int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int b
   int rc = tasks_chol(h, nt, pt, &tl, &tr);
   if (rc) return rc;
   GemmParams p{};
-  p.small_k = gemm_small_k(np);
   p.A = mref(Lbuf, np, stride);
   p.B = mref(Lbuf, np, stride);
   p.C = mref(Lbuf, np, stride);
@@ -218,7 +217,6 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
   if (rc) return rc;
   for (int lvl = 0; lvl < ts.steps(); lvl++) {
     GemmParams p{};
-    p.small_k = gemm_small_k(np);
     p.A = mref(Lbuf, np, stride);
     p.B = mref(Lbuf, np, stride);
     p.C = mref(Sbuf, np, stride);
@@ -228,7 +226,6 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
     rc = launch_gemm(h, LAYOUT_TT, EPI_AXPBY, p, ts.count(lvl), batch);
     if (rc) return rc;
     GemmParams q{};
-    q.small_k = gemm_small_k(np);
     q.A = mref(Sbuf, np, stride);
     q.B = mref(Lbuf, np, stride);
     q.C = mref(Lbuf, np, stride);

@@ -24,20 +24,20 @@
 namespace gpb {
 
 #ifndef GPB_DEFAULT_CFG
-#define GPB_DEFAULT_CFG 4
+#define GPB_DEFAULT_CFG 2
 #endif
 constexpr int KC = 16;
-// Four configurations of the same kernel are built (gpb200_set_gemm_config; 4 is the default):
-//   1 Big    128x128 CTA tile, 2x4 warps of 64x32, 4 stages, 1 CTA/SM
-//   2 Small  128x128, 4x4 warps of 32x32, per-warp zero-skipping of triangular operand tiles
-//   3 Half   128x64 CTA tile, 2x2 warps of 64x32, 3 stages, 2 CTAs/SM
-//   4 Half8  128x64 CTA tile, 4x2 warps of 32x32, 3 stages, 2 CTAs/SM  <- default
+// Two configurations of the same kernel are built (gpb200_set_gemm_config; 2 is the default):
+//   1 Big    128x128 CTA tile, 2x4 warps of 64x32, 4 stages, 1 CTA/SM (the first design, kept as the baseline)
+//   2 Half8  128x64 CTA tile, 4x2 warps of 32x32, 3 stages, 2 CTAs/SM
 // With one CTA per SM every per-chunk barrier, prologue and epilogue is a bubble in the DMMA pipe
 // (91.5 % active, profiles/ncu_summary_r01b.md).  Two independent half-tile CTAs per SM cover each
-// other's bubbles (96 %), and with 32x32 warp tiles each sub-partition still has two warps of the other
-// CTA to draw DMMAs from while one CTA sits in a barrier or in its epilogue.  Splitting the tile along n
-// also makes the zero half of a triangular B operand tile skippable for a whole CTA (no warp imbalance).
-template <int WARPS_M_, int WARPS_N_, bool SKIP_, int TN_ = TILE, int STAGES_ = 4, int MINB_ = 1>
+// other's bubbles (95 %), and with 32x32 warp tiles each sub-partition still has two warps of the other
+// CTA to draw DMMAs from while one CTA sits in a barrier or in its epilogue (a 2x2-warp half tile of 64x32
+// warp tiles reached 96 % on the Cholesky update but only 91 % on LAUUM + trace).  Splitting the tile along n
+// also makes the zero half of a triangular B operand tile skippable for a whole CTA; per-warp skipping inside
+// a CTA (a 16-warp 128x128 configuration, round-1 history) cost more than it saved and is gone.
+template <int WARPS_M_, int WARPS_N_, int TN_ = TILE, int STAGES_ = 4, int MINB_ = 1>
 struct GemmCfg {
   static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;  // warp grid over the TILE x TN CTA tile
   static constexpr int TN = TN_;                                // CTA tile extent in n (TILE in m)
@@ -47,22 +47,19 @@ struct GemmCfg {
   static constexpr int NTHREADS = 32 * WARPS_M_ * WARPS_N_;
   static constexpr int NCOPY_A = KC * TILE / 2 / NTHREADS;      // 16-byte copies per thread per stage
   static constexpr int NCOPY_B = KC * TN_ / 2 / NTHREADS;
-  static constexpr bool SKIP = SKIP_;
   static constexpr int STAGES = STAGES_, MINB = MINB_;
   static constexpr int LD_MC_B = TN_ + 4;                       // B stage with n contiguous: [KC][TN+4]
   static constexpr int STAGE_A = TILE * (KC + 4);               // 2560 doubles >= KC * (TILE + 4)
   static constexpr int STAGE_B = TN_ * (KC + 4);                // >= KC * (TN + 4)
   static constexpr int SMEM_BYTES = STAGES_ * (STAGE_A + STAGE_B) * (int)sizeof(double);
 };
-using CfgBig = GemmCfg<2, 4, false>;
-using CfgHalf = GemmCfg<2, 2, false, 64, 3, 2>;
-using CfgHalf8 = GemmCfg<4, 2, false, 64, 3, 2>;
-using CfgSmall = GemmCfg<4, 4, true>;
+using CfgBig = GemmCfg<2, 4>;
+using CfgHalf8 = GemmCfg<4, 2, 64, 3, 2>;
 constexpr int LD_MC = TILE + 4;  // operand with the tile index contiguous: stage[KC][132]
 constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
 constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 5 * 16 + 8;
-static_assert(EPI_SCRATCH_DOUBLES * 8 <= CfgHalf::SMEM_BYTES, "epilogue scratch must fit the pipeline buffers");
-static_assert((CfgHalf::LD_MC_B % 16) == 4 && (LD_MC % 16) == 4 && (LD_KC % 16) == 4, "conflict-free fragment loads");
+static_assert(EPI_SCRATCH_DOUBLES * 8 <= CfgHalf8::SMEM_BYTES, "epilogue scratch must fit the pipeline buffers");
+static_assert((CfgHalf8::LD_MC_B % 16) == 4 && (LD_MC % 16) == 4 && (LD_KC % 16) == 4, "conflict-free fragment loads");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -105,10 +102,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
   const long long lda = p.A.ld, ldb = p.B.ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  // Warp -> sub-tile map: a Latin square over (warp % WARPS_N, warp / WARPS_N), so that every SM
-  // sub-partition (warp % 4) owns one warp of every row band and one of every column band: when a
-  // triangular operand tile lets some warps skip a chunk, the saved DMMAs are spread evenly over the
-  // four tensor pipes.
+  // Warp -> sub-tile map: a Latin square over (warp % WARPS_N, warp / WARPS_N), so that the two warps a
+  // sub-partition (warp % 4) holds of this CTA sit in different column bands (measured 0.5 % faster than the
+  // plain row-major map on the N=4096 step).
   const int wm = (warp / WARPS_N) * WM, wn = (((warp % WARPS_N) + (warp / WARPS_N)) % WARPS_N) * WN;
 
   double acc[NI][MI][2];
@@ -182,36 +178,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
   double af[2][MI], bf[2][NI];
   load_frags(smem, smem + STAGE_DOUBLES, 0, af[0], bf[0]);
 
-  // Chunks whose products are all zero for this warp because an operand tile is triangular.  A
-  // skipping warp runs only the chunk transition (same barrier count), so the full loop body stays
-  // branch-free and software-pipelined.
-  const int tflags = Cfg::SKIP ? task.flags : 0;
-  auto skip_chunk = [&](int kc) -> bool {
-    if (!(tflags & (TF_A_TRI_FIRST | TF_A_TRI_LAST | TF_B_TRI_FIRST | TF_B_TRI_LAST))) return false;
-    const int kl = kc - (nk - TILE / KC);  // chunk index inside the LAST k-tile (>= 0 there)
-    bool sk = false;
-    if ((tflags & TF_A_TRI_FIRST) && kc < TILE / KC && kc * KC + KC - 1 < wm) sk = true;   // zero where k < m
-    const int wnt = n0 + wn;  // warp's first column inside the task's 128x128 tile
-    if ((tflags & TF_B_TRI_FIRST) && kc < TILE / KC && kc * KC + KC - 1 < wnt) sk = true;  // zero where k < n
-    if ((tflags & TF_A_TRI_LAST) && kl >= 0 && kl * KC > wm + WM - 1) sk = true;           // zero where k > m
-    if ((tflags & TF_B_TRI_LAST) && kl >= 0 && kl * KC > wnt + WN - 1) sk = true;          // zero where k > n
-    return sk;
-  };
-
   for (int kc = 0; kc < nk; kc++) {
     const double *sA = smem + (kc % STAGES) * STAGE_PAIR;
     const double *sB = sA + STAGE_DOUBLES;
-    if (skip_chunk(kc)) {  // warp-uniform
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      if (kc + STAGES < nk) load_stage(kc % STAGES, kc + STAGES);
-      cp_async_commit();
-      if (kc + 1 < nk) {
-        const double *nA = smem + ((kc + 1) % STAGES) * STAGE_PAIR;
-        load_frags(nA, nA + STAGE_DOUBLES, 0, af[0], bf[0]);
-      }
-      continue;
-    }
 #pragma unroll
     for (int kk = 0; kk < KC / 4; kk++) {
       const int cur = kk & 1, nxt = cur ^ 1;
@@ -445,9 +414,7 @@ static int smem_setup_cfg(Handle *h) {
 // handle is created (gpb200_create), once per handle, so one process may hold handles on several GPUs.
 int gemm_smem_setup(Handle *h) {
   int rc = smem_setup_cfg<CfgBig>(h);
-  if (!rc) rc = smem_setup_cfg<CfgHalf>(h);
-  if (!rc) rc = smem_setup_cfg<CfgHalf8>(h);
-  return rc ? rc : smem_setup_cfg<CfgSmall>(h);
+  return rc ? rc : smem_setup_cfg<CfgHalf8>(h);
 }
 
 template <class Cfg>
@@ -467,28 +434,18 @@ static int launch_cfg(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParam
   return -2;
 }
 
-// configuration choice: 1 Big, 2 Small (16-warp zero-skipping, short k-loops), 3 Half (two CTAs per SM)
-// Measured on B200 (profiles/bench_configs_r01.json, bench_r01*.json): configuration 4 wins or ties at every
-// size from N=512 (100.2k vs 97.0k evals/s for the zero-skipping 16-warp one) to N=4096 (455 vs 434 for
-// the one-CTA-per-SM one), so it is the default everywhere; the others stay selectable for comparison.
-static int gemm_pick_cfg(const Handle *h, int small_k) {
-  (void)small_k;
-  if (h->gemm_cfg_override) return h->gemm_cfg_override;
-  return GPB_DEFAULT_CFG;
-}
+// configuration choice: 1 Big, 2 Half8 (two CTAs per SM; default -- it wins or ties at every size from N=512
+// to N=4096, profiles/bench_configs_r01.json)
+static int gemm_pick_cfg(const Handle *h) { return h->gemm_cfg_override ? h->gemm_cfg_override : GPB_DEFAULT_CFG; }
 
 // CTAs per 128x128 task of the configuration launch_gemm will pick (the trace epilogues write one
 // partial record per CTA)
-int gemm_nsplit(const Handle *h, int small_k) { return gemm_pick_cfg(h, small_k) >= 3 ? CfgHalf::NSPLIT : 1; }
+int gemm_nsplit(const Handle *h) { return gemm_pick_cfg(h) == 2 ? CfgHalf8::NSPLIT : 1; }
 
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
   if (ntasks <= 0 || batch <= 0) return 0;
-  switch (gemm_pick_cfg(h, p.small_k)) {
-    case 2: return launch_cfg<CfgSmall>(h, layout, epi, p, ntasks, batch);
-    case 3: return launch_cfg<CfgHalf>(h, layout, epi, p, ntasks, batch);
-    case 4: return launch_cfg<CfgHalf8>(h, layout, epi, p, ntasks, batch);
-    default: return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
-  }
+  if (gemm_pick_cfg(h) == 1) return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
+  return launch_cfg<CfgHalf8>(h, layout, epi, p, ntasks, batch);
 }
 
 }  // namespace gpb

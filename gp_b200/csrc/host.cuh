@@ -55,8 +55,6 @@ int tasks_lauum(Handle *h, int nt, TaskList *out);
 
 // ---- engines on padded device buffers ---------------------------------------------------------
 inline MatRef mref(double *p, long long ld, long long stride) { return MatRef{p, ld, stride}; }
-// short k-loops (few tiles per dimension): use the 16-warp zero-skipping GEMM configuration
-inline int gemm_small_k(int np) { return np / TILE <= 12; }
 int chol_panel_tiles(int nt, int batch);
 int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev, double *dvec);
 int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long stride, int batch);

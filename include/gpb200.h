@@ -56,10 +56,9 @@ GPB200_API long long gpb200_graph_replays(gpb200_handle_t h);
  * for batches >= 64, 8-tile panels + right-looking trailing updates for small batches) */
 GPB200_API int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles);
 
-/* tuning/testing knob: GEMM configuration.  0 = automatic; 1 = "Big": 128x128 CTA tile, 8 warps, one CTA
- * per SM; 2 = "Small": 16 warps of 32x32 with triangular zero-skipping (short k-loops, up to 12 tiles per
- * dimension); 3 = "Half": 128x64 CTA tile, 4 warps, two CTAs per SM.  GPB200_GEMM_CFG in the environment
- * sets the same knob at handle creation. */
+/* tuning/testing knob: GEMM configuration.  0 = default (2); 1 = one 128x128 CTA per SM (8 warps of 64x32,
+ * the first design); 2 = two 128x64 half-tile CTAs per SM (8 warps of 32x32 each).  GPB200_GEMM_CFG in the
+ * environment sets the same knob at handle creation. */
 GPB200_API int gpb200_set_gemm_config(gpb200_handle_t h, int cfg);
 
 /* per-kernel-class timing with CUDA events on the handle's stream (used by bench.py for the

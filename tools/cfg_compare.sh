@@ -1,6 +1,6 @@
 #!/bin/bash
-# bench the headline step under each long-k GEMM configuration (1 = Big, 3 = Half: two CTAs per SM)
-for c in ${CFGS:-1 3}; do
+# bench the headline step under each long-k GEMM configuration (1 = one 128x128 CTA per SM, 2 = two half-tile CTAs per SM)
+for c in ${CFGS:-1 2}; do
   GPB200_GEMM_CFG=$c python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg$c.json 2> gpurun_out/bench_cfg$c.err
   python - <<PY
 import json
