@@ -150,3 +150,24 @@ def test_c2_joint_derivative_lml_and_gradient_n512(handle):
     # batching changes no bit
     l1, g1, _ = handle.lml_grad_deriv_batched(t, yy, th[2:3], 1e-6)
     assert l1[0] == lml[2] and np.array_equal(g1[0], grad[2])
+
+
+def test_headline_n4096_scale_and_homogeneity_properties(handle):
+    # size-independent properties at the headline size, no oracle needed:
+    #  (1) K(c alpha, rho, c sigma) = c^2 K  =>  lml(c y | c alpha, rho, c sigma) = lml(y | alpha, rho, sigma) - n log c,
+    #      d/drho unchanged, d/dalpha and d/dsigma divided by c;
+    #  (2) alpha dL/dalpha + sigma dL/dsigma = y^T K^-1 y - n  (K homogeneous of degree 2 in (alpha, sigma)), with
+    #      y^T K^-1 y recovered from two evaluations at y and 2y:  lml(2y) - lml(y) = -1.5 y^T K^-1 y
+    n = 4096
+    x, y = o.synth_xy(n, 5)
+    th = np.array([[0.9, 1.1, 0.3]])
+    c = 3.0
+    l1, g1, _ = handle.lml_grad_batched(x, y, th)
+    l2, g2, _ = handle.lml_grad_batched(x, c * y, th * np.array([c, 1.0, c]))
+    assert abs((l2[0] - l1[0]) + n * np.log(c)) <= 1e-10 * abs(l1[0])
+    assert abs(g2[0, 1] - g1[0, 1]) <= 1e-9 * abs(g1[0, 1])
+    assert abs(g2[0, 0] * c - g1[0, 0]) <= 1e-9 * abs(g1[0, 0]) and abs(g2[0, 2] * c - g1[0, 2]) <= 1e-9 * abs(g1[0, 2])
+    l3, _, _ = handle.lml_grad_batched(x, 2.0 * y, th)
+    quad = -(l3[0] - l1[0]) / 1.5
+    lhs = th[0, 0] * g1[0, 0] + th[0, 2] * g1[0, 2]
+    assert abs(lhs - (quad - n)) <= 1e-9 * max(abs(quad), n)

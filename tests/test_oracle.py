@@ -251,3 +251,38 @@ def test_lml_and_gradient_agree_with_scikit_learn_gpr():
         assert np.max(np.abs(gr - chain)) <= 1e-9 * np.max(np.abs(chain))
         rv2, rg2 = o.lml_grad_lapack(x, y, a, r, s)
         assert abs(v - rv2) <= 1e-11 * abs(rv2) and np.max(np.abs(rg2 - rg)) <= 1e-9 * np.max(np.abs(rg))
+
+
+# ---- property-based checks of the restatement (hypothesis) -------------------------------------------
+def test_oracle_properties_hold_for_random_inputs():
+    """Size-independent properties of the LML path, over random sizes / inputs / hyper-parameters:
+    permutation invariance, gradient vs central differences, the sigma-gradient identity
+    alpha dL/dalpha + sigma dL/dsigma = y^T K^-1 y - n (K is homogeneous of degree 2 in (alpha, sigma)),
+    and NumPy <-> C agreement."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from oracle import c_oracle as c
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(n=st.integers(2, 60), seed=st.integers(0, 10_000), alpha=st.floats(0.3, 2.0), rho=st.floats(0.3, 3.0),
+           sigma=st.floats(0.1, 0.8))
+    def check(n, seed, alpha, rho, sigma):
+        rng = np.random.default_rng(seed)
+        x = np.sort(rng.uniform(0, 0.3 * n, n)); y = rng.standard_normal(n)
+        v, g = o.lml_grad(x, y, alpha, rho, sigma)
+        perm = rng.permutation(n)
+        vp, gp = o.lml_grad(x[perm], y[perm], alpha, rho, sigma)
+        assert abs(v - vp) <= 1e-10 * max(1.0, abs(v)) and np.max(np.abs(g - gp)) <= 1e-8 * max(1.0, np.max(np.abs(g)))
+        th = np.array([alpha, rho, sigma])
+        for i in range(3):
+            h = 1e-6 * th[i]
+            tp, tm = th.copy(), th.copy(); tp[i] += h; tm[i] -= h
+            fd = (o.lml(x, y, *tp) - o.lml(x, y, *tm)) / (2 * h)
+            assert abs(fd - g[i]) <= 2e-5 * max(1.0, abs(g[i]))
+        K = o.gram_se(x, alpha, rho, sigma * sigma)
+        quad = float(y @ np.linalg.solve(K, y))
+        assert abs(alpha * g[0] + sigma * g[2] - (quad - n)) <= 1e-8 * max(1.0, abs(quad))
+        cv, cg, info = c.lml_grad(x, y, th)
+        assert info == 0 and abs(cv - v) <= 1e-10 * max(1.0, abs(v)) and np.max(np.abs(cg - g)) <= 1e-8 * max(1.0, np.max(np.abs(g)))
+
+    check()
