@@ -123,3 +123,51 @@ inline double gp_lml_dd(const Eigen::Matrix<double, Eigen::Dynamic, 1>& t, const
   gpb200_stan::eval_dd(t, dx, sf2, l2, s2, lml, nullptr);
   return lml;
 }
+
+// ---- joint derivative observations (design_notes.Rmd:25-46; BASELINE config 2): y_stack = (y, y', y'') on the
+// grid t, noise = per-block sd (1 to 3 entries), jitter 1e-6 as in R/ode_gp_library.R:30:
+//
+//   functions { real gp_lml_joint(vector t, vector y_stack, real alpha, real rho, vector noise); }
+//   model     { target += gp_lml_joint(t, append_row(y, append_row(yp, ypp)), alpha, rho, noise); }
+namespace gpb200_stan {
+inline void eval_joint(const Eigen::VectorXd& t, const Eigen::VectorXd& y, double alpha, double rho, const double* noise,
+                       int nblocks, double& lml, double* grad) {
+  if (nblocks < 1 || nblocks > 3 || y.size() != t.size() * nblocks)
+    throw std::domain_error("gp_lml_joint: y_stack must hold 1 to 3 blocks of length(t) observations");
+  double theta[5] = {alpha, rho, 0.0, 0.0, 0.0};
+  for (int b = 0; b < nblocks; b++) theta[2 + b] = noise[b];
+  double g[5];
+  int info = 0;
+  const int rc = gpb200_lml_grad_deriv_batched(handle(), (int)t.size(), /*order0=*/0, nblocks, 1, t.data(), 0, y.data(), 0,
+                                               theta, 1e-6, grad != nullptr, &lml, g, &info);
+  if (rc < 0) throw std::runtime_error(std::string("gp_lml_joint: ") + gpb200_last_error(handle()));
+  if (info > 0) throw std::domain_error("gp_lml_joint: covariance is not positive definite (pivot " + std::to_string(info) + ")");
+  if (grad) for (int q = 0; q < 2 + nblocks; q++) grad[q] = g[q];
+}
+}  // namespace gpb200_stan
+
+template <typename T0__, typename T1__, typename T2__>
+typename boost::math::tools::promote_args<T0__, T1__, T2__>::type
+gp_lml_joint(const Eigen::Matrix<double, Eigen::Dynamic, 1>& t, const Eigen::Matrix<double, Eigen::Dynamic, 1>& y_stack,
+             const T0__& alpha, const T1__& rho, const Eigen::Matrix<T2__, Eigen::Dynamic, 1>& noise, std::ostream* pstream__) {
+  using stan::math::value_of;
+  const int nb = (int)noise.size();
+  double nz[3] = {0.0, 0.0, 0.0};
+  for (int b = 0; b < nb && b < 3; b++) nz[b] = value_of(noise.data()[b]);
+  double lml, g[5];
+  gpb200_stan::eval_joint(t, y_stack, value_of(alpha), value_of(rho), nz, nb, lml, g);
+  std::vector<stan::math::var> operands;
+  std::vector<double> partials;
+  gpb200_stan::add_operand(operands, partials, alpha, g[0]);
+  gpb200_stan::add_operand(operands, partials, rho, g[1]);
+  for (int b = 0; b < nb; b++) gpb200_stan::add_operand(operands, partials, noise.data()[b], g[2 + b]);
+  return stan::math::precomputed_gradients(lml, operands, partials);
+}
+
+inline double gp_lml_joint(const Eigen::Matrix<double, Eigen::Dynamic, 1>& t,
+                           const Eigen::Matrix<double, Eigen::Dynamic, 1>& y_stack, const double& alpha, const double& rho,
+                           const Eigen::Matrix<double, Eigen::Dynamic, 1>& noise, std::ostream* pstream__) {
+  double lml;
+  gpb200_stan::eval_joint(t, y_stack, alpha, rho, noise.data(), (int)noise.size(), lml, nullptr);
+  return lml;
+}
