@@ -10,13 +10,13 @@ extern "C" int gpb200_normal_fill(gpb200_handle_t h, unsigned long long seed, un
   if (offset & 1ULL) BAD_ARG(h, 3, "normal_fill: offset must be even (normals are generated in Box-Muller pairs)");
   if (len == 0) return 0;
   if (h->device_ptrs) {
-    RC(launch_normal_fill(h, seed, offset, len, (int)std::min<long long>(len, 1 << 30), len, out));
+    RC(launch_normal_fill(h, seed, offset, len, len, len, out));
     return 0;
   }
   Arena a;
   RC(ws_reserve(h, pad256((size_t)len * 8) + 256, &a));
   double *d = a.take<double>((size_t)len);
-  RC(launch_normal_fill(h, seed, offset, len, (int)std::min<long long>(len, 1 << 30), len, d));
+  RC(launch_normal_fill(h, seed, offset, len, len, len, d));
   RC(from_device(h, d, out, (size_t)len * sizeof(double)));
   return finish(h);
 }

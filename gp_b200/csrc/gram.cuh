@@ -59,7 +59,7 @@ int launch_hermite(Handle *h, long long len, int n, const double *y1, const doub
 int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2);
 
 // rng.cu
-int launch_normal_fill(Handle *h, unsigned long long seed, unsigned long long offset, long long len, int rows,
+int launch_normal_fill(Handle *h, unsigned long long seed, unsigned long long offset, long long len, long long rows,
                        long long ld, double *out);
 int launch_add_mean_transpose(Handle *h, int m, int ndraws, const double *X, long long ldx, const double *mu,
                               double *out, long long ldo);

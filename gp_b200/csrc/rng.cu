@@ -33,7 +33,7 @@ __device__ __forceinline__ double u53(unsigned a, unsigned b) {
 // out[e] for e in [0, len): normal number e of stream `seed` (+ `offset` elements).  Counter q = e / 2
 // yields the Box-Muller pair (e even: cos branch, e odd: sin branch).  ld / rows lay the stream out as
 // a column-major matrix with padding rows left untouched (rows == ld for a flat vector).
-__global__ void normal_fill_kernel(unsigned long long seed, unsigned long long offset, long long len, int rows,
+__global__ void normal_fill_kernel(unsigned long long seed, unsigned long long offset, long long len, long long rows,
                                    long long ld, double *__restrict__ out) {
   const long long npairs = (len + 1) / 2;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < npairs; q += (long long)gridDim.x * blockDim.x) {
@@ -50,7 +50,7 @@ __global__ void normal_fill_kernel(unsigned long long seed, unsigned long long o
   }
 }
 
-int launch_normal_fill(Handle *h, unsigned long long seed, unsigned long long offset, long long len, int rows,
+int launch_normal_fill(Handle *h, unsigned long long seed, unsigned long long offset, long long len, long long rows,
                        long long ld, double *out) {
   if (len <= 0) return 0;
   const long long npairs = (len + 1) / 2;
