@@ -38,6 +38,7 @@ SIGNATURES = {
     "gpb200_set_gemm_config": (C.c_int, [_h, C.c_int]),
     "gpb200_set_profiling": (C.c_int, [_h, C.c_int]),
     "gpb200_get_profile": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
+    "gpb200_debug_bench_panel": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gpb200_kernel_eval": (C.c_int, [_h, C.c_int, _ll, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     "gpb200_gram_outer": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                     C.c_void_p, C.c_int]),
@@ -192,6 +193,13 @@ class Handle:
 
     def set_profiling(self, on: bool):
         self._check(self.lib.gpb200_set_profiling(self._h, int(bool(on))), "set_profiling")
+
+    def debug_bench_panel(self, what, nt, batch, reps=5):
+        """Mean device time (ms) of one panel kernel launch: what 0 POTRF tile, 1 TRSM tiles, 2 tile inverses."""
+        ms = np.zeros(1)
+        self._check(self.lib.gpb200_debug_bench_panel(self._h, int(what), int(nt), int(batch), int(reps), _ptr(ms)),
+                    "debug_bench_panel")
+        return float(ms[0])
 
     def get_profile(self):
         ms = np.zeros(6); cnt = np.zeros(6, dtype=np.int64)

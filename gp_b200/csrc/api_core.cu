@@ -28,10 +28,25 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return -1000; }
+  {
+    int lo = 0, hi = 0;  // numerically lowest value = highest priority
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->pstream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return -1000; }
+  }
+  const char *cp = getenv("GPB200_CHOL_PANEL");  // same meaning as gpb200_set_chol_panel_tiles
+  if (cp && cp[0] >= '0' && cp[0] <= '9') h->chol_panel_override = atoi(cp);
+  const char *la = getenv("GPB200_LOOKAHEAD");
+  if (la && la[0] == '0') h->lookahead = 0;
+  const char *qw = getenv("GPB200_QUARTER_WAVES");
+  if (qw && qw[0] >= '0' && qw[0] <= '9') h->quarter_below_waves = atoi(qw);
   const char *gc = getenv("GPB200_GEMM_CFG");  // tuning knob, same meaning as gpb200_set_gemm_config
-  if (gc && gc[0] >= '0' && gc[0] <= '2') h->gemm_cfg_override = gc[0] - '0';
+  if (gc && gc[0] >= '0' && gc[0] <= '3') h->gemm_cfg_override = gc[0] - '0';
   const char *tp = getenv("GPB200_TRSM_PIPELINED");
   if (tp && tp[0] == '0') h->trsm_pipelined = 0;
+  const char *pv = getenv("GPB200_PANEL_V1");
+  if (pv && pv[0] == '1') h->panel_impl = 1;
+  const char *tm = getenv("GPB200_TRSM_MT");
+  if (tm && (tm[0] == '1' || tm[0] == '2' || tm[0] == '4')) h->trsm_mt_override = tm[0] - '0';
   const char *ng = getenv("GPB200_NO_GRAPH");
   if (ng && ng[0] == '1') h->graphs_enabled = 0;
   *out = h;
@@ -44,6 +59,9 @@ extern "C" int gpb200_destroy(gpb200_handle_t h) {
   cudaStreamSynchronize(h->stream);
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   if (h->gstream) { cudaStreamSynchronize(h->gstream); cudaStreamDestroy(h->gstream); }
+  if (h->pstream) { cudaStreamSynchronize(h->pstream); cudaStreamDestroy(h->pstream); }
+  for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->g_in) cudaEventDestroy(h->g_in);
   if (h->g_out) cudaEventDestroy(h->g_out);
   if (h->ws) cudaFree(h->ws);
@@ -84,7 +102,7 @@ extern "C" int gpb200_set_chol_panel_tiles(gpb200_handle_t h, int tiles) {
 
 // test/tuning knob: 0 default, 1 one 128x128 CTA per SM, 2 two 128x64 half-tile CTAs per SM
 extern "C" int gpb200_set_gemm_config(gpb200_handle_t h, int cfg) {
-  if (!h || cfg < 0 || cfg > 2) return -1;
+  if (!h || cfg < 0 || cfg > 3) return -1;
   h->gemm_cfg_override = cfg;
   return 0;
 }
@@ -266,7 +284,7 @@ extern "C" int gpb200_potrf(gpb200_handle_t h, int n, double *A, int lda) {
     lds = n;
   }
   RC(launch_pack(h, n, n, src, lds, np, np, Lbuf, 1, 0.0));
-  RC(chol_batched(h, Lbuf, np, (long long)np * np, n, 1, info, nullptr));
+  RC(chol_batched(h, Lbuf, np, (long long)np * np, n, 1, info));
   int hinfo = 0;
   RC(read_info(h, info, &hinfo));
   if (h->device_ptrs) {
@@ -447,5 +465,58 @@ extern "C" int gpb200_mvn_chol_lpdf(gpb200_handle_t h, int n, const double *y, c
   } else {
     *lp = v;
   }
+  return 0;
+}
+
+
+// =================================================================================================
+// tuning aid: times one panel kernel in isolation on `batch` synthetic SE Gram matrices of nt x nt tiles
+// (CUDA events around each launch; the matrices are rebuilt before every repetition).
+//   what = 0  POTRF of the first diagonal tile           (1 CTA per item)
+//   what = 1  TRSM of the nt-1 tiles below it             (after the POTRF)
+//   what = 2  inverse of the nt diagonal tiles            (after a full factorisation)
+// ms_out[0] = mean kernel time in ms.  DEVICE work only; not part of the reference-facing surface.
+// =================================================================================================
+extern "C" int gpb200_debug_bench_panel(gpb200_handle_t h, int what, int nt, int batch, int reps, double *ms_out) {
+  CHECK_H(h);
+  if (nt < 1 || batch < 1 || reps < 1 || what < 0 || what > 2) BAD_ARG(h, 2, "debug_bench_panel: bad arguments");
+  const int np = nt * TILE, n = np;
+  const long long mat = (long long)np * np;
+  Arena a;
+  RC(ws_reserve(h, pad256(mat * 8) * batch * 2 + pad256(n * 8) + 4096, &a));
+  double *Lbuf = a.take<double>((size_t)mat * batch), *Wbuf = a.take<double>((size_t)mat * batch);
+  double *dx = a.take<double>(n), *dth = a.take<double>(3 * (size_t)batch);
+  int *info = a.take<int>(batch);
+  if (!info) BAD_ARG(h, 1002, "debug_bench_panel: workspace exhausted");
+  std::vector<double> x(n), th(3 * (size_t)batch);
+  for (int i = 0; i < n; i++) x[i] = 0.05 * i;
+  for (int b = 0; b < batch; b++) { th[3 * b] = 1.0; th[3 * b + 1] = 1.0; th[3 * b + 2] = 0.3; }
+  GPB_CUDA(h, cudaMemcpyAsync(dx, x.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+  GPB_CUDA(h, cudaMemcpyAsync(dth, th.data(), th.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  GPB_CUDA(h, cudaMemsetAsync(info, 0, batch * sizeof(int), h->stream));
+  cudaEvent_t e0, e1;
+  GPB_CUDA(h, cudaEventCreate(&e0));
+  GPB_CUDA(h, cudaEventCreate(&e1));
+  double total = 0.0;
+  int rc = 0;
+  for (int r = 0; r < reps + 1 && !rc; r++) {  // repetition 0 is a warm-up
+    rc = launch_gram_se_batched(h, n, np, dx, 0, dth, 0.0, 1, Lbuf, mat, batch);
+    if (!rc && what >= 1) rc = launch_potrf_tile(h, Lbuf, np, mat, 0, n, batch, info);
+    if (!rc && what == 2) rc = chol_batched(h, Lbuf, np, mat, n, batch, info);
+    if (rc) break;
+    cudaEventRecord(e0, h->stream);
+    if (what == 0) rc = launch_potrf_tile(h, Lbuf, np, mat, 0, n, batch, info);
+    else if (what == 1) rc = launch_trsm_tiles(h, Lbuf, np, mat, 0, nt - 1, batch);
+    else rc = launch_tile_inverse(h, Lbuf, Wbuf, np, mat, nt, batch);
+    cudaEventRecord(e1, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = -1000;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0) total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc) return rc;
+  ms_out[0] = total / reps;
   return 0;
 }

@@ -25,7 +25,7 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
   TaskList tl;
   RC(tasks_lauum(h, nt, &tl));
   const int ntasks = tl.count(0);
-  const int nparts = ntasks * 2;  // trace partial records per item: one per CTA, at most two CTAs per tile
+  const int nparts = ntasks * 4;  // trace partial records per item: one per CTA, at most four CTAs per tile
 
   // chunk the batch so that the resident set fits the workspace limit.  cudaMemGetInfo costs
   // milliseconds with tens of GB allocated, so it is only consulted when the workspace must grow.
@@ -66,7 +66,7 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
       const double *cx = dx + (long long)b0 * xs, *cy = dy + (long long)b0 * ys, *cth = dth + (long long)b0 * ts;
       if (sp.deriv) RC(launch_gram_deriv_batched(h, ng, sp.order0, sp.nblocks, np, cx, xs, cth, ts, jitter, 1, Lbuf, mat, bc));
       else RC(launch_gram_se_batched(h, n, np, cx, xs, cth, jitter, 1, Lbuf, mat, bc));
-      RC(chol_batched(h, Lbuf, np, mat, n, bc, dinfo + b0, nullptr));
+      RC(chol_batched(h, Lbuf, np, mat, n, bc, dinfo + b0));
       RC(extract_diag(h, np, Lbuf, mat, dvec, bc));
       if (want_grad) {
         RC(trtri_batched(h, Lbuf, Sbuf, np, mat, bc));
@@ -91,17 +91,17 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
         else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
       }
       if (sp.deriv)
-        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h), cth, dlml + b0,
+        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, ntasks, bc), cth, dlml + b0,
                                  dgrad + (long long)b0 * ts, bc));
       else
-        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h), cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
+        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, ntasks, bc), cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
     }
     return 0;
   };
 
   // Small problems are launch-latency bound (tens of launches of a few microseconds each): replay
   // them as one CUDA graph on the handle's own stream, ordered against the caller's stream by events.
-  const bool use_graph = h->graphs_enabled && !h->profiling && Bc == B && nt <= 16 && (long long)B * nt * nt <= 4096;
+  const bool use_graph = h->graphs_enabled && !h->profiling && Bc == B && nt <= 64 && (long long)B * nt * nt <= 4096;
   cudaStream_t user_stream = h->stream;
   if (use_graph) {
     GPB_CUDA(h, cudaEventRecord(h->g_in, user_stream));
@@ -121,14 +121,13 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
       long long jbits;
       memcpy(&jbits, &jitter, sizeof(jbits));
       const std::vector<long long> key = {n, B, want_grad, xs, ys, jbits, (long long)(uintptr_t)h->ws, h->chol_panel_override,
-                                          sp.deriv, sp.order0, sp.nblocks, h->gemm_cfg_override};
+                                          sp.deriv, sp.order0, sp.nblocks, h->gemm_cfg_override, h->lookahead, h->lookahead_max_batch,
+                                          h->panel_impl, h->trsm_mt_override, h->quarter_below_waves, h->trsm_pipelined};
       auto it = h->graphs.find(key);
       if (it == h->graphs.end()) {
-        // task lists allocate and synchronise on first use: make sure they exist before the capture
-        TaskList t1, t2, t3;
-        const int pt = h->chol_panel_override > 0 ? std::min(nt, h->chol_panel_override) : chol_panel_tiles(nt, B);
-        if ((rc = tasks_chol(h, nt, pt, &t1, &t2))) break;
-        if (nt > 1 && (rc = tasks_trtri(h, nt, &t1, &t3))) break;
+        // task lists allocate and synchronise on first use, which a capture does not allow: a first uncaptured
+        // pass builds every list the sequence needs (its results are simply overwritten by the replay)
+        if ((rc = run_sequence())) break;
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = -1000; break; }
         const long long before = h->launches;
@@ -253,7 +252,7 @@ int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, const 
   GPB_CUDA(h, cudaMemcpyAsync(dls, ls_host, sizeof(double) * P, cudaMemcpyHostToDevice, h->stream));
   GPB_CUDA(h, cudaStreamSynchronize(h->stream));  // ls_host may be a stack temporary
   RC(launch_gram_tangent(h, n, np, dx, alpha, dls, dadd, mode, Lbuf, Dbuf, st, P));
-  RC(chol_batched(h, Lbuf, np, st, n, P, info, nullptr));
+  RC(chol_batched(h, Lbuf, np, st, n, P, info));
   GPB_CUDA(h, cudaMemcpyAsync(info_out_host, info, sizeof(int) * P, cudaMemcpyDeviceToHost, h->stream));
   GPB_CUDA(h, cudaMemcpyAsync(Lkeep, Lbuf, mat * P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   RC(trtri_batched(h, Lbuf, Sbuf, np, st, P));
@@ -417,7 +416,7 @@ int condition_device(Handle *h, Arena &a, int n, int m, const double *K, long lo
   RC(launch_pack(h, n, n, K, ldk, np, np, Lbuf, 1, noise_var));
   RC(launch_pack(h, m, n, Ks, ldks, mp, np, Ksp, 0, 0.0));
   RC(launch_pack(h, m, m, Kss, ldkss, mp, mp, Cp, 0, 0.0));
-  RC(chol_batched(h, Lbuf, np, (long long)mat, n, 1, info, nullptr));
+  RC(chol_batched(h, Lbuf, np, (long long)mat, n, 1, info));
   RC(read_info(h, info, hinfo));
   RC(trtri_batched(h, Lbuf, Sbuf, np, (long long)mat, 1));
   RC(launch_trmv_lower_n(h, np, Lbuf, 0, rhs, 0, n, z, 0, 1));

@@ -64,7 +64,7 @@ extern "C" int gpb200_mvrnorm(gpb200_handle_t h, int ndraws, int m, const double
   }
   GPB_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int), h->stream));
   RC(launch_pack(h, m, m, dS, ld, mp, mp, Lbuf, 1, jitter));
-  RC(chol_batched(h, Lbuf, mp, (long long)mat, m, 1, info, nullptr));
+  RC(chol_batched(h, Lbuf, mp, (long long)mat, m, 1, info));
   int hinfo = 0;
   RC(read_info(h, info, &hinfo));
   if (hinfo) return hinfo;

@@ -61,8 +61,11 @@ struct Handle {
   long long launches = 0;
   long long ws_limit = 0;
   int chol_panel_override = 0;
-  int gemm_cfg_override = 0;  // 0 default (2), 1 one 128x128 CTA per SM, 2 two 128x64 half-tile CTAs per SM
+  int gemm_cfg_override = 0;  // 0 automatic, 1 one 128x128 CTA per SM, 2 two 128x64 half-tile CTAs per SM, 3 64x64 quarter-tile CTAs
+  int quarter_below_waves = 2;  // automatic choice: quarter tiles while the half-tile grid is below this many waves of 2 x 148 CTAs
   int trsm_pipelined = 1;     // 0: one tile per CTA (the first TRSM tile kernel); env GPB200_TRSM_PIPELINED
+  int panel_impl = 0;         // 0: left-looking shared-memory panel kernels (round 2); 1: the round-1 register-tile kernels (env GPB200_PANEL_V1)
+  int trsm_mt_override = 0;   // tuning knob: 8-row mma tiles per warp of trsm_ll_kernel (1, 2, 4); env GPB200_TRSM_MT
   char err[512] = {0};
   // grow-only device workspace
   void *ws = nullptr;
@@ -78,6 +81,20 @@ struct Handle {
   std::map<std::vector<long long>, GraphEntry> graphs;
   int graphs_enabled = 1;
   long long graph_replays = 0;
+  // look-ahead Cholesky for small batches: the panel chain (update of the next block column, POTRF, TRSM) runs on
+  // a high-priority side stream while the rest of the trailing update runs on the handle's stream
+  cudaStream_t pstream = nullptr;
+  std::vector<cudaEvent_t> sync_events;
+  int lookahead = 1;            // env GPB200_LOOKAHEAD=0 disables
+  int lookahead_max_batch = 8;  // batches up to this size take the look-ahead schedule
+  cudaEvent_t sync_event(size_t i) {
+    while (sync_events.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      sync_events.push_back(e);
+    }
+    return sync_events[i];
+  }
   // optional per-kernel-class timing with CUDA events on the handle's stream (bench.py roofline)
   int profiling = 0;
   struct ProfRec { int cls; cudaEvent_t e0, e1; };
@@ -143,7 +160,7 @@ enum GemmEpi { EPI_AXPBY = 0, EPI_TRACE = 1, EPI_TRACE_DERIV = 2 };
 
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch);
 int gemm_smem_setup(Handle *h);
-int gemm_nsplit(const Handle *h);
+int gemm_nsplit(const Handle *h, int ntasks, int batch);
 
 // panel kernels (panel.cu)
 int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n,

@@ -172,8 +172,93 @@ int chol_panel_tiles(int nt, int batch) {
   return 8;
 }
 
-int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev, double *dvec) {
+// Trailing-update task lists of the look-ahead schedule: after panel [p0, p1) is factored, list 1 updates the block
+// columns of the NEXT panel (the panel chain waits for it), list 2 everything to the right of that.
+static int tasks_chol_lookahead(Handle *h, int nt, int pt, TaskList *la1, TaskList *la2) {
+  const long long k1 = tkey(TK_CHOL_LA1, nt, pt), k2 = tkey(TK_CHOL_LA2, nt, pt);
+  if (cached(h, k1, la1) && cached(h, k2, la2)) return 0;
+  std::vector<TileTask> t1, t2;
+  std::vector<int> o1(1, 0), o2(1, 0);
+  for (int p0 = 0; p0 < nt; p0 += pt) {
+    const int p1 = std::min(nt, p0 + pt), p2 = std::min(nt, p1 + pt);
+    for (int jj = p1; jj < nt; jj++)
+      for (int i = jj; i < nt; i++)
+        (jj < p2 ? t1 : t2).push_back({i * TILE, p0 * TILE, jj * TILE, p0 * TILE, i * TILE, jj * TILE, (p1 - p0) * TILE, i == jj});
+    o1.push_back((int)t1.size());
+    o2.push_back((int)t2.size());
+  }
+  int rc = upload_tasks(h, k1, t1, o1, la1);
+  if (rc) return rc;
+  return upload_tasks(h, k2, t2, o2, la2);
+}
+
+bool chol_uses_lookahead(const Handle *h, int nt, int batch) {
+  return h->lookahead && h->pstream && batch <= h->lookahead_max_batch && nt >= 3;
+}
+int chol_lookahead_panel(const Handle *h, int nt) {
+  return h->chol_panel_override > 0 ? std::min(nt, h->chol_panel_override) : 1;
+}
+
+// Look-ahead schedule (small batches; one matrix does not fill the GPU and the panel chain of one POTRF tile and
+// one TRSM wave per block column is what bounds the factorisation):
+//   side stream P :  [in-panel left-looking update] -> POTRF -> TRSM   per block column of the panel
+//   main stream T :  wait(panel) -> update of the next panel's columns -> signal P -> update of the rest
+// so panel p+1 is factored while the bulk of panel p's trailing update still runs.  All writes to a block column
+// are ordered: its trailing updates happen on T in program order, and P touches it only after T's signal.
+static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev) {
+  const int nt = np / TILE, pt = chol_lookahead_panel(h, nt);
+  TaskList tl, tr, la1, la2;
+  int rc = tasks_chol(h, nt, pt, &tl, &tr);
+  if (rc) return rc;
+  rc = tasks_chol_lookahead(h, nt, pt, &la1, &la2);
+  if (rc) return rc;
+  GemmParams p{};
+  p.A = mref(Lbuf, np, stride);
+  p.B = mref(Lbuf, np, stride);
+  p.C = mref(Lbuf, np, stride);
+  p.C0 = mref(Lbuf, np, stride);
+  p.alpha = -1.0;
+  p.beta = 1.0;
+  cudaStream_t T = h->stream, P = h->pstream;
+  struct Restore { Handle *h; cudaStream_t s; ~Restore() { h->stream = s; } } restore{h, T};
+  size_t ev = 0;
+  GPB_CUDA(h, cudaEventRecord(h->sync_event(ev), T));
+  GPB_CUDA(h, cudaStreamWaitEvent(P, h->sync_event(ev), 0));
+  ev++;
+  int panel = 0;
+  for (int p0 = 0; p0 < nt; p0 += pt, panel++) {
+    const int p1 = std::min(nt, p0 + pt);
+    h->stream = P;
+    for (int j = p0; j < p1; j++) {
+      if (tl.count(j) > 0) {
+        p.tasks = tl.at(j);
+        if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(j), batch))) return rc;
+      }
+      if ((rc = launch_potrf_tile(h, Lbuf, np, stride, j, n, batch, info_dev))) return rc;
+      if ((rc = launch_trsm_tiles(h, Lbuf, np, stride, j, nt - 1 - j, batch))) return rc;
+    }
+    GPB_CUDA(h, cudaEventRecord(h->sync_event(ev), P));
+    h->stream = T;
+    GPB_CUDA(h, cudaStreamWaitEvent(T, h->sync_event(ev), 0));
+    ev++;
+    if (p1 < nt) {
+      p.tasks = la1.at(panel);
+      if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, la1.count(panel), batch))) return rc;
+      GPB_CUDA(h, cudaEventRecord(h->sync_event(ev), T));
+      GPB_CUDA(h, cudaStreamWaitEvent(P, h->sync_event(ev), 0));
+      ev++;
+      if (la2.count(panel) > 0) {
+        p.tasks = la2.at(panel);
+        if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, la2.count(panel), batch))) return rc;
+      }
+    }
+  }
+  return 0;  // T has waited for the last panel: the side stream is joined
+}
+
+int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev) {
   const int nt = np / TILE;
+  if (chol_uses_lookahead(h, nt, batch)) return chol_lookahead(h, Lbuf, np, stride, n, batch, info_dev);
   const int pt = h->chol_panel_override > 0 ? std::min(nt, h->chol_panel_override) : chol_panel_tiles(nt, batch);
   TaskList tl, tr;
   int rc = tasks_chol(h, nt, pt, &tl, &tr);
@@ -202,7 +287,6 @@ int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int b
       if (rc) return rc;
     }
   }
-  (void)dvec;
   return 0;
 }
 

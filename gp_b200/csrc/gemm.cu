@@ -37,29 +37,36 @@ constexpr int KC = 16;
 // warp tiles reached 96 % on the Cholesky update but only 91 % on LAUUM + trace).  Splitting the tile along n
 // also makes the zero half of a triangular B operand tile skippable for a whole CTA; per-warp skipping inside
 // a CTA (a 16-warp 128x128 configuration, round-1 history) cost more than it saved and is gone.
-template <int WARPS_M_, int WARPS_N_, int TN_ = TILE, int STAGES_ = 4, int MINB_ = 1>
+template <int WARPS_M_, int WARPS_N_, int TN_ = TILE, int STAGES_ = 4, int MINB_ = 1, int TM_ = TILE>
 struct GemmCfg {
-  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;  // warp grid over the TILE x TN CTA tile
-  static constexpr int TN = TN_;                                // CTA tile extent in n (TILE in m)
-  static constexpr int NSPLIT = TILE / TN_;                     // CTAs per 128x128 task
-  static constexpr int WM = TILE / WARPS_M_, WN = TN_ / WARPS_N_;  // warp tile
+  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;  // warp grid over the TM x TN CTA tile
+  static constexpr int TM = TM_, TN = TN_;                      // CTA tile extents in m and n
+  static constexpr int NSPLIT_M = TILE / TM_, NSPLIT_N = TILE / TN_;
+  static constexpr int NSPLIT = NSPLIT_M * NSPLIT_N;            // CTAs per 128x128 task
+  static constexpr int WM = TM_ / WARPS_M_, WN = TN_ / WARPS_N_;  // warp tile
   static constexpr int MI = WM / 8, NI = WN / 8;                // 8x8 mma tiles per warp
   static constexpr int NTHREADS = 32 * WARPS_M_ * WARPS_N_;
-  static constexpr int NCOPY_A = KC * TILE / 2 / NTHREADS;      // 16-byte copies per thread per stage
+  static constexpr int NCOPY_A = KC * TM_ / 2 / NTHREADS;       // 16-byte copies per thread per stage
   static constexpr int NCOPY_B = KC * TN_ / 2 / NTHREADS;
   static constexpr int STAGES = STAGES_, MINB = MINB_;
+  static constexpr int LD_MC_A = TM_ + 4;                       // A stage with m contiguous: [KC][TM+4]
   static constexpr int LD_MC_B = TN_ + 4;                       // B stage with n contiguous: [KC][TN+4]
-  static constexpr int STAGE_A = TILE * (KC + 4);               // 2560 doubles >= KC * (TILE + 4)
+  static constexpr int STAGE_A = TM_ * (KC + 4);                // >= KC * (TM + 4)
   static constexpr int STAGE_B = TN_ * (KC + 4);                // >= KC * (TN + 4)
   static constexpr int SMEM_BYTES = STAGES_ * (STAGE_A + STAGE_B) * (int)sizeof(double);
 };
 using CfgBig = GemmCfg<2, 4>;
 using CfgHalf8 = GemmCfg<4, 2, 64, 3, 2>;
-constexpr int LD_MC = TILE + 4;  // operand with the tile index contiguous: stage[KC][132]
+// 3 Quarter: 64x64 CTA tile, 2x2 warps of 32x32, 3 stages, 3 CTAs/SM.  Four CTAs per 128x128 task: a launch
+// with few tasks (one large matrix, batch 1: the latency path) still covers the GPU, the zero half of a triangular
+// operand tile is skipped for A as well as for B, and the redundant upper-right quadrant of a symmetric diagonal
+// tile is not computed at all (its CTA exits).
+using CfgQuarter = GemmCfg<2, 2, 64, 3, 3, 64>;
 constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
 constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 5 * 16 + 8;
 static_assert(EPI_SCRATCH_DOUBLES * 8 <= CfgHalf8::SMEM_BYTES, "epilogue scratch must fit the pipeline buffers");
-static_assert((CfgHalf8::LD_MC_B % 16) == 4 && (LD_MC % 16) == 4 && (LD_KC % 16) == 4, "conflict-free fragment loads");
+static_assert(EPI_SCRATCH_DOUBLES * 8 <= CfgQuarter::SMEM_BYTES, "epilogue scratch must fit the pipeline buffers");
+static_assert((CfgHalf8::LD_MC_B % 16) == 4 && (CfgBig::LD_MC_A % 16) == 4 && (CfgQuarter::LD_MC_A % 16) == 4 && (LD_KC % 16) == 4, "conflict-free fragment loads");
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -82,19 +89,31 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
   constexpr int STAGES = Cfg::STAGES, TN = Cfg::TN, LD_MC_B = Cfg::LD_MC_B;
   constexpr int STAGE_DOUBLES = Cfg::STAGE_A, STAGE_PAIR = Cfg::STAGE_A + Cfg::STAGE_B;
   extern __shared__ __align__(16) double smem[];
+  constexpr int TM = Cfg::TM, LD_MC = Cfg::LD_MC_A;
   TileTask task = p.tasks[blockIdx.x / Cfg::NSPLIT];
-  const int n0 = (Cfg::NSPLIT > 1) ? (int)(blockIdx.x % Cfg::NSPLIT) * TN : 0;
-  if (Cfg::NSPLIT > 1) {  // this CTA owns columns [n0, n0 + TN) of the task's 128x128 tile
+  const int split = (Cfg::NSPLIT > 1) ? (int)(blockIdx.x % Cfg::NSPLIT) : 0;
+  const int m0 = (Cfg::NSPLIT_M > 1) ? (split / Cfg::NSPLIT_N) * TM : 0;
+  const int n0 = (Cfg::NSPLIT_N > 1) ? (split % Cfg::NSPLIT_N) * TN : 0;
+  // symmetric diagonal tile: the upper-right quadrant mirrors the lower-left one and no consumer reads it
+  const bool sym_skip = Cfg::NSPLIT_M > 1 && (task.flags & TF_DIAG) && m0 < n0;
+  if (Cfg::NSPLIT > 1) {  // this CTA owns rows [m0, m0 + TM) x columns [n0, n0 + TN) of the task's 128x128 tile
+    if (A_KC) task.a_c += m0; else task.a_r += m0;
     if (B_KC) task.b_c += n0; else task.b_r += n0;
+    task.c_r += m0;
     task.c_c += n0;
-    // A triangular B operand tile is all zero over half of its k-range for one of the two column
-    // halves: that half simply contracts over 64 fewer k (uniform for the whole CTA).
-    if ((task.flags & TF_B_TRI_FIRST) && n0 >= TILE / 2) {  // zero where k_local < n_local: skip the first 64 k
+    // A triangular operand tile is all zero over half of its k-range for one of the two halves: that CTA
+    // simply contracts over 64 fewer k (uniform for the whole CTA).
+    const bool skip_first = (Cfg::NSPLIT_N > 1 && (task.flags & TF_B_TRI_FIRST) && n0 >= TILE / 2) ||  // zero where k_local < n_local
+                            (Cfg::NSPLIT_M > 1 && (task.flags & TF_A_TRI_FIRST) && m0 >= TILE / 2);    // zero where k_local < m_local
+    const bool skip_last = (Cfg::NSPLIT_N > 1 && (task.flags & TF_B_TRI_LAST) && n0 < TILE / 2) ||     // zero where k_local > n_local
+                           (Cfg::NSPLIT_M > 1 && (task.flags & TF_A_TRI_LAST) && m0 < TILE / 2);       // zero where k_local > m_local
+    if (skip_first) {
       if (A_KC) task.a_r += TILE / 2; else task.a_c += TILE / 2;
       if (B_KC) task.b_r += TILE / 2; else task.b_c += TILE / 2;
       task.k_len -= TILE / 2;
     }
-    if ((task.flags & TF_B_TRI_LAST) && n0 < TILE / 2) task.k_len -= TILE / 2;  // zero where k_local > n_local
+    if (skip_last) task.k_len -= TILE / 2;
+    if (sym_skip) task.k_len = 0;
   }
   const long long b = blockIdx.y;
   const double *__restrict__ A = p.A.p + b * p.A.stride;
@@ -122,7 +141,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
   for (int r = 0; r < NCOPY_A; r++) {
     const int idx = tid + NTHREADS * r;
     if (!A_KC) {
-      const int k = idx >> 6, m2 = idx & 63;
+      const int k = idx / (TM / 2), m2 = idx % (TM / 2);
       srcA[r] = A + (task.a_r + 2 * m2) + (long long)(task.a_c + k) * lda;
       dstA[r] = k * LD_MC + 2 * m2;
     } else {
@@ -206,6 +225,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
   }
   cp_async_wait<0>();
 
+  if (sym_skip) {  // uniform for the CTA
+    if (EPI != EPI_AXPBY && tid < (EPI == EPI_TRACE_DERIV ? 8 : 4))
+      p.partial[((long long)b * gridDim.x + blockIdx.x) * (EPI == EPI_TRACE_DERIV ? 8 : 4) + tid] = 0.0;
+    return;
+  }
   if (EPI == EPI_AXPBY) {
     double *__restrict__ C = p.C.p + b * p.C.stride;
     const double *__restrict__ C0 = p.C0.p ? p.C0.p + b * p.C0.stride : nullptr;
@@ -238,9 +262,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
     const int ng = p.n_grid;
     const double *x = p.x + b * p.x_stride;
     const double *av = p.avec + b * p.a_stride;
-    for (int q = tid; q < TILE + TN; q += NTHREADS) {
-      const bool row = q < TILE;
-      const int ql = row ? q : q - TILE;
+    for (int q = tid; q < TM + TN; q += NTHREADS) {
+      const bool row = q < TM;
+      const int ql = row ? q : q - TM;
       const int i = (row ? task.c_r : task.c_c) + ql;
       const int gi = i - (i >= ng ? ng : 0) - (i >= 2 * ng ? ng : 0);
       (row ? xr : xc)[ql] = (i < p.n) ? x[gi] : 0.0;
@@ -287,7 +311,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
         }
       }
     }
-    const double w = diag_tile ? 1.0 : 2.0;
+    const double w = (diag_tile && (Cfg::NSPLIT_M == 1 || m0 == n0)) ? 1.0 : 2.0;  // a diagonal quadrant / full diagonal tile holds both (i,j) and (j,i)
     s_k *= w;
     s_dk *= w;
 #pragma unroll
@@ -317,9 +341,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
     double *red = smem + 4 * TILE;
     const double *x = p.x + b * p.x_stride;
     const double *av = p.avec + b * p.a_stride;
-    for (int q = tid; q < TILE + TN; q += NTHREADS) {
-      const bool row = q < TILE;
-      const int ql = row ? q : q - TILE;
+    for (int q = tid; q < TM + TN; q += NTHREADS) {
+      const bool row = q < TM;
+      const int ql = row ? q : q - TM;
       const int i = (row ? task.c_r : task.c_c) + ql;
       (row ? xr : xc)[ql] = (i < p.n) ? x[i] : 0.0;
       (row ? ar : ac)[ql] = (i < p.n) ? av[i] : 0.0;
@@ -358,7 +382,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
         }
       }
     }
-    const double w = diag_tile ? 1.0 : 2.0;
+    const double w = (diag_tile && (Cfg::NSPLIT_M == 1 || m0 == n0)) ? 1.0 : 2.0;  // a diagonal quadrant / full diagonal tile holds both (i,j) and (j,i)
     s_se *= w;
     s_d2 *= w;
 #pragma unroll
@@ -414,7 +438,8 @@ static int smem_setup_cfg(Handle *h) {
 // handle is created (gpb200_create), once per handle, so one process may hold handles on several GPUs.
 int gemm_smem_setup(Handle *h) {
   int rc = smem_setup_cfg<CfgBig>(h);
-  return rc ? rc : smem_setup_cfg<CfgHalf8>(h);
+  if (!rc) rc = smem_setup_cfg<CfgHalf8>(h);
+  return rc ? rc : smem_setup_cfg<CfgQuarter>(h);
 }
 
 template <class Cfg>
@@ -434,17 +459,27 @@ static int launch_cfg(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParam
   return -2;
 }
 
-// configuration choice: 1 Big, 2 Half8 (two CTAs per SM; default -- it wins or ties at every size from N=512
-// to N=4096, profiles/bench_configs_r01.json)
-static int gemm_pick_cfg(const Handle *h) { return h->gemm_cfg_override ? h->gemm_cfg_override : GPB_DEFAULT_CFG; }
+// configuration choice: 1 Big, 2 Half8 (two CTAs per SM; wins or ties at every batched size from N=512 to N=4096,
+// profiles/bench_configs_r01.json), 3 Quarter (64x64 CTAs).  Automatic: Quarter while the launch is too small to
+// give every SM its two Half8 CTAs (the single-matrix latency path), Half8 otherwise.
+int gemm_pick_cfg(const Handle *h, int ntasks, int batch) {
+  if (h->gemm_cfg_override) return h->gemm_cfg_override;
+  if (GPB_DEFAULT_CFG != 2) return GPB_DEFAULT_CFG;
+  return ((long long)ntasks * batch * CfgHalf8::NSPLIT < 2LL * 148 * h->quarter_below_waves) ? 3 : 2;
+}
 
-// CTAs per 128x128 task of the configuration launch_gemm will pick (the trace epilogues write one
-// partial record per CTA)
-int gemm_nsplit(const Handle *h) { return gemm_pick_cfg(h) == 2 ? CfgHalf8::NSPLIT : 1; }
+// CTAs per 128x128 task of the configuration launch_gemm will pick for this launch (the trace epilogues write
+// one partial record per CTA)
+int gemm_nsplit(const Handle *h, int ntasks, int batch) {
+  const int c = gemm_pick_cfg(h, ntasks, batch);
+  return c == 3 ? CfgQuarter::NSPLIT : (c == 2 ? CfgHalf8::NSPLIT : 1);
+}
 
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
   if (ntasks <= 0 || batch <= 0) return 0;
-  if (gemm_pick_cfg(h) == 1) return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
+  const int c = gemm_pick_cfg(h, ntasks, batch);
+  if (c == 1) return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
+  if (c == 3) return launch_cfg<CfgQuarter>(h, layout, epi, p, ntasks, batch);
   return launch_cfg<CfgHalf8>(h, layout, epi, p, ntasks, batch);
 }
 

@@ -33,7 +33,7 @@ inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 int ws_reserve(Handle *h, size_t bytes, Arena *a);
 
 // ---- tile task lists (host-built once per tile count, cached on the device) ---------------------
-enum TaskKind { TK_CHOL = 1, TK_CHOL_TRAIL, TK_TRTRI_S, TK_TRTRI_W, TK_LAUUM, TK_TAN_T1, TK_TAN_A, TK_TAN_LDOT, TK_COND_V,
+enum TaskKind { TK_CHOL = 1, TK_CHOL_TRAIL, TK_CHOL_LA1, TK_CHOL_LA2, TK_TRTRI_S, TK_TRTRI_W, TK_LAUUM, TK_TAN_T1, TK_TAN_A, TK_TAN_LDOT, TK_COND_V,
                 TK_COND_COV, TK_MUL_WB, TK_MUL_WTB, TK_MUL_LZ };
 
 struct TaskList {
@@ -56,7 +56,9 @@ int tasks_lauum(Handle *h, int nt, TaskList *out);
 // ---- engines on padded device buffers ---------------------------------------------------------
 inline MatRef mref(double *p, long long ld, long long stride) { return MatRef{p, ld, stride}; }
 int chol_panel_tiles(int nt, int batch);
-int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev, double *dvec);
+bool chol_uses_lookahead(const Handle *h, int nt, int batch);
+int chol_lookahead_panel(const Handle *h, int nt);
+int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev);
 int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long stride, int batch);
 int extract_diag(Handle *h, int np, const double *L, long long stride, double *dvec, int batch);
 

@@ -19,90 +19,6 @@ __device__ __forceinline__ void dmma884p(double (&c)[2], double a, double b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// POTRF of one 128x128 tile.  256 threads = 16x16 grid; thread (ti,tj) owns A[ti+16a][tj+16b].
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
-potrf_tile_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
-                  int n, int *info) {
-  __shared__ double col[2][TILE];
-  __shared__ int s_info;
-  const int tid = threadIdx.x;
-  const int ti = tid & 15, tj = tid >> 4;
-  double *T = Lbase + (long long)blockIdx.x * stride + diag_off;
-  double r[8][8];
-#pragma unroll
-  for (int b = 0; b < 8; b++)
-#pragma unroll
-    for (int a = 0; a < 8; a++) r[a][b] = T[(ti + 16 * a) + (long long)(tj + 16 * b) * ld];
-  if (tid == 0) s_info = 0;
-
-  for (int k = 0; k < TILE; k++) {
-    const int kb = k >> 4, kt = k & 15;
-    double *cbuf = col[k & 1];
-    if (tj == kt) {
-      // this thread column owns column k: publish it (rows >= k are meaningful)
-#pragma unroll
-      for (int b = 0; b < 8; b++)
-        if (b == kb) {
-#pragma unroll
-          for (int a = 0; a < 8; a++) cbuf[ti + 16 * a] = r[a][b];
-        }
-    }
-    __syncthreads();
-    const double piv = cbuf[k];
-    if (!(piv > 0.0)) {
-      // non-positive (or NaN) pivot: record the first one, keep going so the CTA stays in step
-      if (tid == 0 && s_info == 0) s_info = index_base + k + 1;
-    }
-    const double dgl = sqrt(piv);
-    const double inv = 1.0 / dgl;
-    double li[8], lj[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) li[a] = cbuf[ti + 16 * a] * inv;
-#pragma unroll
-    for (int b = 0; b < 8; b++) lj[b] = cbuf[tj + 16 * b] * inv;
-#pragma unroll
-    for (int b = 0; b < 8; b++) {
-      if (b >= kb) {
-        const int j = tj + 16 * b;
-#pragma unroll
-        for (int a = 0; a < 8; a++) {
-          if (a >= b) {  // i >= j can only hold when a >= b (ti,tj < 16), refined below
-            const int i = ti + 16 * a;
-            if (j > k && i >= j) r[a][b] = fma(-li[a], lj[b], r[a][b]);
-          }
-        }
-      }
-    }
-    if (tj == kt) {
-#pragma unroll
-      for (int b = 0; b < 8; b++)
-        if (b == kb) {
-#pragma unroll
-          for (int a = 0; a < 8; a++) {
-            const int i = ti + 16 * a;
-            if (i > k) r[a][b] = li[a];
-            else if (i == k) r[a][b] = dgl;
-          }
-        }
-    }
-  }
-  // write back: lower triangle = L, strict upper = 0 (Eigen matrixL() convention)
-#pragma unroll
-  for (int b = 0; b < 8; b++)
-#pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int i = ti + 16 * a, j = tj + 16 * b;
-      T[i + (long long)j * ld] = (i >= j) ? r[a][b] : 0.0;
-    }
-  __syncthreads();
-  if (tid == 0 && s_info != 0 && s_info <= n) {
-    // keep the smallest index over tiles (tiles are processed in increasing order, so first wins)
-    if (info[blockIdx.x] == 0) info[blockIdx.x] = s_info;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // POTRF of one 128x128 tile, blocked (v2): right-looking over sixteen 8-column blocks with the tile
 // register-resident in mma accumulator layout (warp w owns rows 16w..16w+15, like the TRSM kernel):
 //   1. the warp that owns the 8x8 diagonal block factors it with warp shuffles (8 dependent steps)
@@ -491,17 +407,274 @@ trsm_tiles_pipelined_kernel(const double *Ldiag_base, double *Cbase, long long l
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Round-2 panel kernels: left-looking over 8-column blocks with the tile resident in SHARED memory.
+//
+// The round-1 kernels keep the 128x128 tile in registers in mma accumulator layout, which forces the
+// sixteen block steps to be fully unrolled (register arrays need static indices): potrf_tile_kernel_v2
+// is 28 000 SASS instructions, each executed once -- it runs at instruction-fetch speed (46 us per tile,
+// 5 600 cycles per block step against ~1 500 of dependent arithmetic).  With the tile in shared memory
+// every index is dynamic, the block loop stays rolled (a few hundred instructions), and the left-looking
+// order needs no register-resident trailing matrix at all:
+//
+//   for cb = 0..15:   P  = T[:, 8cb:8cb+8] - T[:, 0:8cb] * T[8cb:8cb+8, 0:8cb]^T     DMMA, own rows
+//                     D  = chol(P[8cb:8cb+8, :])   every warp redundantly, in registers, no shuffles
+//                     T[below, 8cb:8cb+8] = P[below] D^-T    true substitution, one row per lane
+//
+// potrf_tile_ll_kernel: two block barriers per step (the diagonal block must be complete before it is
+// factored; the solved panel must be visible before the next step's update).
+// trsm_ll_kernel: the rows of X = C L^-T are independent, so each warp runs its own rows through all
+// sixteen steps with no block barrier at all; a CTA takes 32, 64 or 128 rows so that a single large
+// matrix (batch 1) still spreads one block column over the whole GPU.
+// ------------------------------------------------------------------------------------------------
+constexpr int LD_T = TILE + 4;  // column-major tile in shared memory, 132: conflict-free mma fragment reads
+constexpr int POTRF_LL_SMEM_BYTES = TILE * LD_T * (int)sizeof(double);
+
+// Cholesky of an 8x8 block held (lower part) in registers; every lane computes the same thing.
+// inv[k] = 1 / L[k][k]; bad = first k with a non-positive (or NaN) pivot, -1 if none.
+__device__ __forceinline__ void factor8_regs(double (&d)[8][8], double (&inv)[8], int &bad) {
+  bad = -1;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const double piv = d[k][k];
+    if (!(piv > 0.0) && bad < 0) bad = k;
+    const double r = rsqrt(piv);
+    inv[k] = r;
+    d[k][k] = piv * r;
+#pragma unroll
+    for (int i = k + 1; i < 8; i++) d[i][k] *= r;
+#pragma unroll
+    for (int j = k + 1; j < 8; j++)
+#pragma unroll
+      for (int i = j; i < 8; i++) d[i][j] = fma(-d[i][k], d[j][k], d[i][j]);
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+potrf_tile_ll_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
+                     int n, int *info) {
+  extern __shared__ __align__(16) double sm[];
+  double *Ts = sm;  // Ts[c * LD_T + r] = T[r][c]
+  __shared__ double Dsm[64];  // the updated diagonal block of the current step, Dsm[c * 8 + r]
+  __shared__ int s_info;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double *T = Lbase + (long long)blockIdx.x * stride + diag_off;
+  const int r0 = warp * 16;
+  if (tid == 0) s_info = 0;
+
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+    const int c = idx >> 6, r2 = idx & 63;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(Ts + c * LD_T + 2 * r2);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(T + 2 * r2 + (long long)c * ld) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+
+#pragma unroll 1
+  for (int cb = 0; cb < 16; cb++) {
+    const int c0 = 8 * cb;
+    const bool active = (2 * warp + 1) >= cb;  // this warp still has rows at or below the diagonal block
+    // ---- 1. left-looking update of the warp's rows of block column cb -------------------------------
+    if (active && cb > 0) {
+      double s[2][2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) s[mt][ch][0] = s[mt][ch][1] = 0.0;
+      const bool m0 = (2 * warp) >= cb;  // the upper m-tile is still below / on the diagonal block
+      const double *pa = Ts + t * LD_T + r0 + g;
+      const double *pb = Ts + t * LD_T + c0 + g;
+      for (int kb = 0; kb < cb; kb++) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          const int ko = (8 * kb + 4 * ch) * LD_T;
+          const double b = pb[ko];
+          if (m0) dmma884p(s[0][ch], pa[ko], b);
+          dmma884p(s[1][ch], pa[ko + 8], b);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        if (mt == 0 && !m0) continue;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          double *p = Ts + (c0 + 2 * t + e) * LD_T + r0 + mt * 8 + g;
+          *p = (*p - s[mt][0][e]) - s[mt][1][e];
+        }
+      }
+    }
+    if (warp == (cb >> 1)) {
+      // publish the updated diagonal block apart from the tile: its rows are overwritten in place by their
+      // owner in step 2 while the other warps may still be reading it
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < 2; e++) Dsm[(2 * t + e) * 8 + g] = Ts[(c0 + 2 * t + e) * LD_T + c0 + g];
+    }
+    __syncthreads();
+    // ---- 2. diagonal block (redundantly per lane) + substitution, one row per lane -------------------
+    if (active) {
+      double d[8][8], inv[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+#pragma unroll
+        for (int i = j; i < 8; i++) d[i][j] = Dsm[j * 8 + i];
+      int bad;
+      factor8_regs(d, inv, bad);
+      if (bad >= 0 && warp == (cb >> 1) && lane == 0 && s_info == 0) s_info = index_base + c0 + bad + 1;
+      const int r = r0 + lane;
+      if (lane < 16 && r >= c0) {
+        double x[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) x[c] = Ts[(c0 + c) * LD_T + r];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          double sv = x[c];
+#pragma unroll
+          for (int cp = 0; cp < c; cp++) sv = fma(-x[cp], d[c][cp], sv);
+          x[c] = sv * inv[c];
+        }
+        const int i = r - c0;  // < 8: a row of the diagonal block itself (the formula above reproduces L_D)
+#pragma unroll
+        for (int c = 0; c < 8; c++) Ts[(c0 + c) * LD_T + r] = (i < 8 && c > i) ? 0.0 : x[c];
+      }
+    }
+    __syncthreads();
+  }
+
+  // write back: lower triangle = L, strict upper = 0 (Eigen matrixL() convention)
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+    const int c = idx >> 6, r = 2 * (idx & 63);
+    const double2 v = *reinterpret_cast<const double2 *>(Ts + c * LD_T + r);
+    *reinterpret_cast<double2 *>(T + r + (long long)c * ld) = make_double2(r >= c ? v.x : 0.0, r + 1 >= c ? v.y : 0.0);
+  }
+  if (tid == 0 && s_info != 0 && s_info <= n) {
+    if (info[blockIdx.x] == 0) info[blockIdx.x] = s_info;
+  }
+}
+
+// X L^T = C for ROWS = 32 MT consecutive rows of a block column (MODE-0 semantics of trsm_tile_kernel),
+// four warps of 8 MT rows each.  blockIdx.x = row chunk, blockIdx.y = batch item.
+template <int MT>
+struct TrsmLL {
+  static constexpr int ROWS = 32 * MT;
+  static constexpr int LD_C = ROWS + 4;
+  static constexpr int SMEM_BYTES = (LPK_DOUBLES + TILE + TILE * LD_C) * (int)sizeof(double);
+};
+
+template <int MT>
+__global__ void __launch_bounds__(128)
+trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long stride, long long diag_off, long long c_off) {
+  constexpr int ROWS = TrsmLL<MT>::ROWS, LD_C = TrsmLL<MT>::LD_C;
+  extern __shared__ __align__(16) double sm[];
+  double *Lp = sm;                  // packed lower triangle of the diagonal tile (see lpk_off / lpk_ld)
+  double *invd = sm + LPK_DOUBLES;  // 1 / L[n][n]
+  double *Cs = invd + TILE;         // Cs[c * LD_C + r] = C[r][c]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double *Ld = Ldiag_base + (long long)blockIdx.y * stride + diag_off;
+  double *Ct = Cbase + (long long)blockIdx.y * stride + c_off + (long long)blockIdx.x * ROWS;
+
+  auto cp16 = [](double *dst, const double *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+  };
+#pragma unroll 1
+  for (int cb = 0; cb < 16; cb++) {
+    const int rows2 = (TILE - 8 * cb) / 2;
+    for (int idx = tid; idx < 8 * rows2; idx += 128) {
+      const int kk = idx / rows2, r2 = idx - kk * rows2;
+      cp16(Lp + lpk_off(cb) + kk * lpk_ld(cb) + 2 * r2, Ld + (8 * cb + 2 * r2) + (long long)(8 * cb + kk) * ld);
+    }
+  }
+  for (int idx = tid; idx < TILE * ROWS / 2; idx += 128) {
+    const int c = idx / (ROWS / 2), r2 = idx - c * (ROWS / 2);
+    cp16(Cs + c * LD_C + 2 * r2, Ct + 2 * r2 + (long long)c * ld);
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  if (tid < TILE) invd[tid] = 1.0 / Lp[lpk_off(tid >> 3) + (tid & 7) * lpk_ld(tid >> 3) + (tid & 7)];
+  __syncthreads();
+
+  const int r0 = warp * 8 * MT;
+#pragma unroll 1
+  for (int cb = 0; cb < 16; cb++) {
+    const int c0 = 8 * cb;
+    const double *Lg = Lp + lpk_off(cb);
+    const int ldg = lpk_ld(cb);
+    if (cb > 0) {
+      // S = X[rows, 0:c0] * L[c0:c0+8, 0:c0]^T, two independent accumulation chains per m-tile
+      double s[MT][2][2];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) s[mt][ch][0] = s[mt][ch][1] = 0.0;
+      const double *pa = Cs + t * LD_C + r0 + g;
+      for (int kb = 0; kb < cb; kb++) {
+        const double *Lk = Lp + lpk_off(kb) + (c0 + g - 8 * kb);
+        const int ldk = lpk_ld(kb);
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          const double b = Lk[(4 * ch + t) * ldk];
+          const double *a = pa + (8 * kb + 4 * ch) * LD_C;
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) dmma884p(s[mt][ch], a[8 * mt], b);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          double *p = Cs + (c0 + 2 * t + e) * LD_C + r0 + mt * 8 + g;
+          *p = (*p - s[mt][0][e]) - s[mt][1][e];
+        }
+      __syncwarp();
+    }
+    // substitution against the 8x8 diagonal block, one row per lane
+    if (lane < 8 * MT) {
+      const int r = r0 + lane;
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) x[c] = Cs[(c0 + c) * LD_C + r];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        double sv = x[c];
+#pragma unroll
+        for (int cp = 0; cp < c; cp++) sv = fma(-x[cp], Lg[cp * ldg + c], sv);
+        x[c] = sv * invd[c0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) Cs[(c0 + c) * LD_C + r] = x[c];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TILE * ROWS / 2; idx += 128) {
+    const int c = idx / (ROWS / 2), r2 = idx - c * (ROWS / 2);
+    *reinterpret_cast<double2 *>(Ct + 2 * r2 + (long long)c * ld) = *reinterpret_cast<const double2 *>(Cs + c * LD_C + 2 * r2);
+  }
+}
+
 int panel_smem_setup(Handle *h) {
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tiles_pipelined_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_PIPE_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(potrf_tile_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_LL_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<1>::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<2>::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<4>::SMEM_BYTES));
   return 0;
 }
 
 int launch_potrf_tile_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, int index_base,
                          int n, int batch, int *info) {
   ProfScope ps__(h, PC_POTRF);
-  potrf_tile_kernel_v2<<<batch, 256, 0, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
+  if (h->panel_impl == 1)
+    potrf_tile_kernel_v2<<<batch, 256, 0, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
+  else
+    potrf_tile_ll_kernel<<<batch, 256, POTRF_LL_SMEM_BYTES, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
@@ -515,17 +688,26 @@ int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int 
 int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, long long c_off,
                          int ntiles, int batch) {
   if (ntiles <= 0) return 0;
-  // tiles per CTA: as many as still leave every SM several CTAs (the diagonal tile is staged once per CTA and
-  // the next tile's loads hide under the current tile's arithmetic)
   const long long total = (long long)ntiles * batch;
-  const int tpc = total >= 148 * 16 ? 4 : (total >= 148 * 6 ? 2 : 1);
   ProfScope ps__(h, PC_TRSM);
-  if (tpc == 1 || h->trsm_pipelined == 0) {
-    dim3 grid(ntiles, batch);
-    trsm_tile_kernel<0><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, 0, c_off, TILE);
+  if (h->panel_impl == 1) {
+    // round-1 kernels: tiles per CTA as many as still leave every SM several CTAs
+    const int tpc = total >= 148 * 16 ? 4 : (total >= 148 * 6 ? 2 : 1);
+    if (tpc == 1 || h->trsm_pipelined == 0) {
+      dim3 grid(ntiles, batch);
+      trsm_tile_kernel<0><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, 0, c_off, TILE);
+    } else {
+      dim3 grid((ntiles + tpc - 1) / tpc, batch);
+      trsm_tiles_pipelined_kernel<2><<<grid, 256, TRSM_PIPE_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off, ntiles, tpc);
+    }
   } else {
-    dim3 grid((ntiles + tpc - 1) / tpc, batch);
-    trsm_tiles_pipelined_kernel<2><<<grid, 256, TRSM_PIPE_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off, ntiles, tpc);
+    // rows per CTA: 32 while that still fits one wave of two CTAs per SM (a single large matrix), else 128
+    int mt = h->trsm_mt_override;
+    if (mt != 1 && mt != 2 && mt != 4) mt = (total * 4 <= 2 * 148) ? 1 : ((total * 2 <= 148) ? 2 : 4);
+    dim3 grid(ntiles * (4 / mt), batch);
+    if (mt == 1) trsm_ll_kernel<1><<<grid, 128, TrsmLL<1>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
+    else if (mt == 2) trsm_ll_kernel<2><<<grid, 128, TrsmLL<2>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
+    else trsm_ll_kernel<4><<<grid, 128, TrsmLL<4>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
   }
   GPB_LAUNCH_CHECK(h);
   return 0;

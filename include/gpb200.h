@@ -67,6 +67,11 @@ GPB200_API int gpb200_set_gemm_config(gpb200_handle_t h, int cfg);
 GPB200_API int gpb200_set_profiling(gpb200_handle_t h, int on);
 GPB200_API int gpb200_get_profile(gpb200_handle_t h, double *ms_out6, long long *count_out6);
 
+/* tuning aid (not a reference interface): times one panel kernel in isolation on `batch` synthetic
+ * matrices of nt x nt 128-tiles.  what: 0 POTRF of a diagonal tile, 1 TRSM of the nt-1 tiles below it,
+ * 2 inverse of the nt diagonal tiles.  ms_out[0] = mean device time per launch (CUDA events). */
+GPB200_API int gpb200_debug_bench_panel(gpb200_handle_t h, int what, int nt, int batch, int reps, double *ms_out);
+
 /* ---- a9: kernel functions ------------------------------------------------------------------ */
 /* kinds of derivative_kernels.R:39-73 (Q = value, R = first derivative, T = second derivative;
  * first letter goes with tj) */
