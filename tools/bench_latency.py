@@ -1,7 +1,7 @@
 """Latency of ONE (or a few) LML+gradient evaluations -- the operating point of the Stan seam
 (stan/gp_lml_stan.hpp -> gpb200_lml_grad, one theta per leapfrog step; models/fit_hyperparameters.stan:18-31
 under pendulum_fit.R:206).  Device-resident inputs, CUDA events over `reps` back-to-back calls, results
-checked against the CPU oracle at N <= 2048.  With arguments "variants" the same measurement is repeated
+With arguments "variants" the same measurement is repeated
 under the tuning knobs (look-ahead off, round-1 panel kernels, panel widths) in child processes."""
 import json
 import os
@@ -13,7 +13,7 @@ import numpy as np
 sys.path.insert(0, ".")
 
 
-def measure(sizes=((4096, 1), (2048, 1), (1024, 1), (100, 1), (4096, 4), (1024, 4), (100, 4)), reps=20, check=True):
+def measure(sizes=((4096, 1), (2048, 1), (1024, 1), (100, 1), (4096, 4), (1024, 4), (100, 4)), reps=20):
     import torch
     from gp_b200 import capi
     dev = torch.device("cuda", 0)
@@ -40,11 +40,7 @@ def measure(sizes=((4096, 1), (2048, 1), (1024, 1), (100, 1), (4096, 4), (1024, 
         e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         rec = {"ms": round(ms, 4), "tflops": round(B * float(n) ** 3 / ms * 1e-9, 2), "info": int(info.abs().sum().item())}
-        if check and n <= 2048:
-            from oracle import gp_oracle as o
-            rv, rg = o.lml_grad(x, y, *th[0])
-            rec["relerr_lml"] = float(abs(lml[0].item() - rv) / abs(rv))
-            rec["relerr_grad"] = float(np.max(np.abs(grad[0].cpu().numpy() - rg)) / np.max(np.abs(rg)))
+        rec["lml0"] = float(lml[0].item())   # parity of this path is asserted in tests/ (the tools never touch the oracle)
         out["n=%d B=%d" % (n, B)] = rec
     h.close()
     return out
