@@ -124,6 +124,44 @@ def synth_inputs(rank):
     return x, y, theta
 
 
+def synth_small(n, B, seed=5):
+    """The same synthetic family at another size (latency extras)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    x = np.sort(rng.uniform(0.0, 0.05 * n, size=n))
+    y = np.sin(x) + 0.5 * np.sin(3.1 * x) + 0.3 * rng.standard_normal(n)
+    theta = np.stack([np.abs(rng.standard_normal(B)) + 0.5, rng.gamma(4.0, 0.25, B) + 0.2, rng.uniform(0.1, 0.5, B)], axis=1)
+    return x, y, theta
+
+
+def measure_latency(h, dev, stream, reps=20):
+    """Latency of ONE evaluation (B = 1) and of a handful (B = 4): the operating point of the Stan seam, where NUTS
+    asks for one log_prob_grad per leapfrog step per chain (models/fit_hyperparameters.stan:18-31 under
+    pendulum_fit.R:206).  Device-resident inputs, CUDA events over `reps` back-to-back calls after 3 warm-ups."""
+    import torch
+    out = {}
+    for n in (4096, 1024, 100):
+        for B in (1, 4):
+            x, y, th = synth_small(n, B)
+            dx = torch.from_numpy(x).to(dev); dy = torch.from_numpy(y).to(dev); dth = torch.from_numpy(th).to(dev)
+            lml = torch.empty(B, dtype=torch.float64, device=dev); grad = torch.empty(B, 3, dtype=torch.float64, device=dev)
+            info = torch.zeros(B, dtype=torch.int32, device=dev)
+            for _ in range(3):
+                h.lml_grad_batched_device(n, B, dx, 0, dy, 0, dth, 0.0, True, lml, grad, info)
+            torch.cuda.synchronize(dev)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                h.lml_grad_batched_device(n, B, dx, 0, dy, 0, dth, 0.0, True, lml, grad, info)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / reps
+            out["n%d_b%d" % (n, B)] = {"ms_per_call": round(ms, 4), "tflops": round(B * float(n) ** 3 / ms * 1e-9, 2),
+                                       "all_pd": int(info.abs().sum().item()) == 0,
+                                       "_check": (x, y, th, lml.cpu().numpy().copy(), grad.cpu().numpy().copy())}
+    return out
+
+
 def cpu_reference_evals_per_sec(n_evals, threads):
     """Times the CPU oracle (LAPACK route) on `n_evals` draws of the N=4096 workload with `threads`
     BLAS threads (torchrun exports OMP_NUM_THREADS=1, so the pool size is set explicitly)."""
@@ -308,6 +346,31 @@ def main():
     d2h = B * 8 + B * 24 + B * 4
     assert np.allclose(hlml.numpy(), lml_dev, rtol=1e-12, atol=0)
 
+    # ---------------- latency extras: one evaluation and a handful (rank 0; the others wait) -----------
+    h.set_pointer_mode(True)
+    latency = measure_latency(h, dev, stream) if rank == 0 else None
+    h.set_pointer_mode(False)
+    barrier()
+
+    # ---------------- checker leg (untimed): every rank compares its FIRST and LAST draw of the timed step, as the
+    # host saw them through the C ABI, with the CPU oracle (the only use of oracle/ in this arm besides cpu_baseline)
+    from oracle import gp_oracle as _o
+    from threadpoolctl import threadpool_limits
+    worst = np.zeros(2)
+    with threadpool_limits(limits=max(1, (os.cpu_count() or 1) // world)):
+        for b in sorted({0, B - 1}):
+            rv, rg = _o.lml_grad_lapack(x, y, *theta[b])
+            worst[0] = max(worst[0], abs(hlml.numpy()[b] - rv) / abs(rv))
+            worst[1] = max(worst[1], float(np.max(np.abs(hgrad.numpy()[b] - rg)) / np.max(np.abs(rg))))
+    wt = torch.from_numpy(worst).to(dev)
+    if world > 1:
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+    worst = wt.cpu().numpy()
+    assert worst[0] <= 1e-9 and worst[1] <= 1e-9, "rank-level parity check against the oracle failed: %r" % (worst,)
+    parity = {"what": "first and last draw of every rank's timed batch vs oracle.lml_grad_lapack, relative error, max over ranks",
+              "ranks": world, "draws_checked_per_rank": len({0, B - 1}), "max_relerr_lml": float(worst[0]),
+              "max_relerr_grad": float(worst[1]), "tolerance": 1e-9}
+
     # ---------------- roofline of the dominant kernel -------------------------------------------
     peak, peak_src = fp64_peak()
     gemm_ms, gemm_count = prof["gemm"]
@@ -343,6 +406,18 @@ def main():
                         "what": "LML-only pass of the same batch (Gram + left-looking tiled Cholesky + forward "
                                 "substitution), N^3/3 flops per evaluation, CUDA events, max over ranks"}
 
+    line["parity"] = parity
+    if latency is not None:
+        if world == 1 and not args.no_cpu_baseline:   # the small latency cases are checked against the oracle too
+            for k, rec in latency.items():
+                lx, ly, lth, llml, lgrad = rec["_check"]
+                if lx.shape[0] <= 1024:
+                    rv, rg = _o.lml_grad(lx, ly, *lth[0])
+                    assert abs(llml[0] - rv) <= 1e-9 * abs(rv) and np.max(np.abs(lgrad[0] - rg)) <= 1e-9 * np.max(np.abs(rg)), k
+        for rec in latency.values():
+            rec.pop("_check")
+        line["latency"] = dict(latency, what="device-resident LML+gradient latency per call, B = 1 and B = 4 (CUDA-graph replay, "
+                                             "look-ahead Cholesky, quarter-tile GEMM CTAs), CUDA events, rank 0")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_evals = 8

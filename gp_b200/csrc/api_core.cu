@@ -24,7 +24,7 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   gpb200_handle_s *h = new (std::nothrow) gpb200_handle_s();
   if (!h) return -1002;
   h->device = device;
-  if (panel_smem_setup(h) || gemm_smem_setup(h)) { delete h; return -1000; }
+  if (panel_smem_setup(h) || gemm_smem_setup(h) || small_smem_setup(h)) { delete h; return -1000; }
   if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return -1000; }
@@ -35,6 +35,8 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   }
   const char *cp = getenv("GPB200_CHOL_PANEL");  // same meaning as gpb200_set_chol_panel_tiles
   if (cp && cp[0] >= '0' && cp[0] <= '9') h->chol_panel_override = atoi(cp);
+  const char *sk = getenv("GPB200_SMALL_KERNEL");
+  if (sk && sk[0] == '0') h->small_kernel = 0;
   const char *la = getenv("GPB200_LOOKAHEAD");
   if (la && la[0] == '0') h->lookahead = 0;
   const char *qw = getenv("GPB200_QUARTER_WAVES");

@@ -29,11 +29,14 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
 
   // chunk the batch so that the resident set fits the workspace limit.  cudaMemGetInfo costs
   // milliseconds with tens of GB allocated, so it is only consulted when the workspace must grow.
-  const size_t per_item = pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)nparts * pw * 8) + 64;
+  // n <= 128: one CTA per item does the whole evaluation in shared memory (small.cu); no O(n^2) workspace at all
+  const bool small = !sp.deriv && lml_small_applies(h, n);
+  const int zks = trmv_split_chunks(np, B);  // k-chunks of the split z = W y (small batches only)
+  const size_t per_item = small ? 0 : pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)nparts * pw * 8) + (zks > 1 ? pad256((size_t)zks * np * 8) : 0) + 64;
   const size_t fixed = pad256((size_t)B * (x_stride ? ng : 0) * 8 + ng * 8) + pad256((size_t)B * (y_stride ? n : 0) * 8 + n * 8) +
                        2 * pad256((size_t)B * ts * 8) + pad256((size_t)B * 8) + pad256((size_t)B * 4) + 4096;
   int Bc = B;
-  if (h->ws_limit > 0 || fixed + per_item * (size_t)B + 8192 > h->ws_bytes) {
+  if (!small && (h->ws_limit > 0 || fixed + per_item * (size_t)B + 8192 > h->ws_bytes)) {
     size_t limit = (size_t)h->ws_limit;
     if (h->ws_limit <= 0) {
       size_t freeb = 0, totalb = 0;
@@ -43,7 +46,7 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
     if (limit < fixed + per_item + 8192) BAD_ARG(h, 1002, "lml_grad_batched: workspace limit too small for one item");
     Bc = (int)std::min<size_t>((size_t)B, (limit - fixed - 8192) / per_item);
   }
-  Bc = std::min(Bc, 65535);  // gridDim.y of the batched launches
+  if (!small) Bc = std::min(Bc, 65535);  // gridDim.y of the batched launches
   Arena a;
   RC(ws_reserve(h, fixed + per_item * (size_t)Bc + 8192, &a));
 
@@ -53,14 +56,20 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
   double *dth = a.take<double>((size_t)B * ts);
   double *dlml = a.take<double>(B), *dgrad = a.take<double>((size_t)B * ts);
   int *dinfo = a.take<int>(B);
-  double *Lbuf = a.take<double>((size_t)Bc * mat), *Sbuf = a.take<double>((size_t)Bc * mat);
-  double *zbuf = a.take<double>((size_t)Bc * np), *abuf = a.take<double>((size_t)Bc * np), *dvec = a.take<double>((size_t)Bc * np);
-  double *partial = a.take<double>((size_t)Bc * nparts * pw);
-  if (!partial) BAD_ARG(h, 1002, "lml_grad_batched: workspace arithmetic error");
+  double *Lbuf = nullptr, *Sbuf = nullptr, *zbuf = nullptr, *abuf = nullptr, *dvec = nullptr, *partial = nullptr, *zpart = nullptr;
+  if (!small) {
+    Lbuf = a.take<double>((size_t)Bc * mat); Sbuf = a.take<double>((size_t)Bc * mat);
+    zbuf = a.take<double>((size_t)Bc * np); abuf = a.take<double>((size_t)Bc * np); dvec = a.take<double>((size_t)Bc * np);
+    partial = a.take<double>((size_t)Bc * nparts * pw);
+    zpart = zks > 1 ? a.take<double>((size_t)Bc * zks * np) : nullptr;
+    if (!partial) BAD_ARG(h, 1002, "lml_grad_batched: workspace arithmetic error");
+  }
+  if (!dinfo) BAD_ARG(h, 1002, "lml_grad_batched: workspace arithmetic error");
 
   // The kernel sequence (everything between staging the inputs and reading the outputs).
   auto run_sequence = [&]() -> int {
     GPB_CUDA(h, cudaMemsetAsync(dinfo, 0, (size_t)B * sizeof(int), h->stream));
+    if (small) return launch_lml_small(h, n, dx, xs, dy, ys, dth, jitter, want_grad, dlml, dgrad, dinfo, B);
     for (int b0 = 0; b0 < B; b0 += Bc) {
       const int bc = std::min(Bc, B - b0);
       const double *cx = dx + (long long)b0 * xs, *cy = dy + (long long)b0 * ys, *cth = dth + (long long)b0 * ts;
@@ -70,7 +79,8 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
       RC(extract_diag(h, np, Lbuf, mat, dvec, bc));
       if (want_grad) {
         RC(trtri_batched(h, Lbuf, Sbuf, np, mat, bc));
-        RC(launch_trmv_lower_n(h, np, Lbuf, mat, cy, ys, n, zbuf, np, bc));
+        if (zks > 1 && zpart) RC(launch_trmv_lower_n_split(h, np, zks, Lbuf, mat, cy, ys, n, zpart, zbuf, np, bc));
+        else RC(launch_trmv_lower_n(h, np, Lbuf, mat, cy, ys, n, zbuf, np, bc));
         RC(launch_trmv_lower_t(h, np, Lbuf, mat, zbuf, np, abuf, np, bc));
         GemmParams p{};
         p.A = mref(Lbuf, np, mat);
@@ -101,7 +111,7 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
 
   // Small problems are launch-latency bound (tens of launches of a few microseconds each): replay
   // them as one CUDA graph on the handle's own stream, ordered against the caller's stream by events.
-  const bool use_graph = h->graphs_enabled && !h->profiling && Bc == B && nt <= 64 && (long long)B * nt * nt <= 4096;
+  const bool use_graph = !small && h->graphs_enabled && !h->profiling && Bc == B && nt <= 64 && (long long)B * nt * nt <= 4096;
   cudaStream_t user_stream = h->stream;
   if (use_graph) {
     GPB_CUDA(h, cudaEventRecord(h->g_in, user_stream));

@@ -85,6 +85,7 @@ struct Handle {
   // a high-priority side stream while the rest of the trailing update runs on the handle's stream
   cudaStream_t pstream = nullptr;
   std::vector<cudaEvent_t> sync_events;
+  int small_kernel = 1;         // one-CTA whole-evaluation kernel for n <= 128 (env GPB200_SMALL_KERNEL=0 disables)
   int lookahead = 1;            // env GPB200_LOOKAHEAD=0 disables
   int lookahead_max_batch = 8;  // batches up to this size take the look-ahead schedule
   cudaEvent_t sync_event(size_t i) {

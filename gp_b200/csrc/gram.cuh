@@ -28,6 +28,9 @@ int launch_approx_basis(Handle *h, int n, int M, double scale, const double *x, 
 // solve.cu
 int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, const double *y, long long y_stride,
                         int n_valid, double *z, long long z_stride, int batch);
+int trmv_split_chunks(int np, int batch);
+int launch_trmv_lower_n_split(Handle *h, int np, int ks, const double *W, long long stride, const double *y, long long y_stride,
+                              int n_valid, double *part, double *z, long long z_stride, int batch);
 int launch_trmv_lower_t(Handle *h, int np, const double *W, long long stride, const double *z, long long z_stride,
                         double *a, long long a_stride, int batch);
 int launch_trsv_blocked(Handle *h, int np, const double *L, const double *Wdiag, long long stride, const double *y,
@@ -57,6 +60,12 @@ int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv,
 int launch_hermite(Handle *h, long long len, int n, const double *y1, const double *y2, const double *k1,
                    const double *k2, double x1, double x2, double l, double *v, double *dvdl);
 int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2);
+
+// small.cu
+int small_smem_setup(Handle *h);
+bool lml_small_applies(const Handle *h, int n);
+int launch_lml_small(Handle *h, int n, const double *x, long long x_stride, const double *y, long long y_stride,
+                     const double *theta, double jitter, int want_grad, double *lml, double *grad, int *info, int batch);
 
 // rng.cu
 int launch_normal_fill(Handle *h, unsigned long long seed, unsigned long long offset, long long len, long long rows,

@@ -8,6 +8,8 @@
 //   finalize                      lml = -n/2 log 2pi - sum log L_ii - 0.5 ||z||^2 and the three
 //                                 gradient components from the fused trace partials
 //   hermite                       covariance.cpp:63-66,85-88 / cubic_interpolated_gp.hpp:63-70
+#include <algorithm>
+
 #include "common.cuh"
 #include "gram.cuh"
 
@@ -53,6 +55,54 @@ __global__ void __launch_bounds__(256) trmv_lower_n_kernel(int np, const double 
   if (half == 1) part[r] = s;
   __syncthreads();
   if (half == 0) z[b * z_stride + i] = s + part[r];
+}
+
+// The same product for a SINGLE matrix (or a few): one 128-row strip per CTA leaves 140 of 148 SMs idle and the
+// N^2/2 read of W crawls at a tenth of HBM speed.  Here blockIdx.y splits each strip's k-range into `ks` chunks of
+// whole tiles; every CTA writes its partial sums to part[(item * ks + chunk) * np + i], and
+// trmv_reduce_parts_kernel adds the chunks in a fixed order (deterministic, no atomics).
+__global__ void __launch_bounds__(256) trmv_lower_n_split_kernel(int np, int ks, const double *__restrict__ W, long long stride,
+                                                                const double *__restrict__ y, long long y_stride,
+                                                                int n_valid, double *__restrict__ part) {
+  __shared__ double psum[TILE];
+  __shared__ double ys[TILE];
+  const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+  const long long b = blockIdx.z;
+  const int ktiles = tile + 1;
+  const int kt0 = (int)((long long)chunk * ktiles / ks), kt1 = (int)((long long)(chunk + 1) * ktiles / ks);
+  const double *Wb = W + b * stride;
+  const double *yb = y + b * y_stride;
+  const int r = tid & 127, half = tid >> 7;
+  const int i = tile * TILE + r;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int kt = kt0; kt < kt1; kt++) {
+    const int k0 = kt * TILE;
+    __syncthreads();
+    if (tid < TILE) ys[tid] = (k0 + tid < n_valid) ? yb[k0 + tid] : 0.0;
+    __syncthreads();
+    const double *wp = Wb + i + (long long)(k0 + half) * np;
+#pragma unroll 4
+    for (int k = half; k < TILE; k += 8) {
+      s0 = fma(wp[0], ys[k], s0);
+      s1 = fma(wp[2LL * np], ys[k + 2], s1);
+      s2 = fma(wp[4LL * np], ys[k + 4], s2);
+      s3 = fma(wp[6LL * np], ys[k + 6], s3);
+      wp += 8LL * np;
+    }
+  }
+  const double s = (s0 + s1) + (s2 + s3);
+  if (half == 1) psum[r] = s;
+  __syncthreads();
+  if (half == 0) part[(b * ks + chunk) * np + i] = s + psum[r];
+}
+
+__global__ void trmv_reduce_parts_kernel(int np, int ks, const double *__restrict__ part, double *__restrict__ z, long long z_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = blockIdx.y;
+  if (i >= np) return;
+  double s = 0.0;
+  for (int c = 0; c < ks; c++) s += part[(b * ks + c) * np + i];
+  z[b * z_stride + i] = s;
 }
 
 // a[k] = sum_{i>=k} W[i,k] z[i]; one warp per column, 16-byte loads, shuffle reduction.
@@ -345,6 +395,30 @@ int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, co
   dim3 grid(np / TILE, batch);
   ProfScope ps__(h, PC_SOLVE);
   trmv_lower_n_kernel<<<grid, 256, 0, h->stream>>>(np, W, stride, y, y_stride, n_valid, z, z_stride);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+// number of k-chunks the split mat-vec uses for this shape (1 = the plain kernel is as good)
+int trmv_split_chunks(int np, int batch) {
+  const int nt = np / TILE;
+  const long long ctas = (long long)nt * batch;
+  if (ctas >= 2 * 148 || nt < 4) return 1;
+  return (int)std::min<long long>(nt, (2 * 148 + ctas - 1) / ctas);
+}
+
+// z = W y with the k-range split over `ks` CTAs per strip; part holds batch * ks * np doubles
+int launch_trmv_lower_n_split(Handle *h, int np, int ks, const double *W, long long stride, const double *y, long long y_stride,
+                              int n_valid, double *part, double *z, long long z_stride, int batch) {
+  {
+    dim3 grid(np / TILE, ks, batch);
+    ProfScope ps__(h, PC_SOLVE);
+    trmv_lower_n_split_kernel<<<grid, 256, 0, h->stream>>>(np, ks, W, stride, y, y_stride, n_valid, part);
+    GPB_LAUNCH_CHECK(h);
+  }
+  dim3 grid2((np + 255) / 256, batch);
+  ProfScope ps__(h, PC_SOLVE);
+  trmv_reduce_parts_kernel<<<grid2, 256, 0, h->stream>>>(np, ks, part, z, z_stride);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

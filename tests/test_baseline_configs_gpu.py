@@ -150,9 +150,9 @@ def test_c2_joint_derivative_lml_and_gradient_n512(handle):
     K = handle.gram_deriv(t, th[0, 0], th[0, 1], th[0, 2:], 1e-6, nblocks=3)
     lp = handle.mvn_chol_lpdf(yy, None, handle.potrf(K))
     assert abs(lml[0] - lp) <= 1e-11 * abs(lp)
-    # batching changes no bit
+    # batching changes nothing beyond rounding (a single item takes the look-ahead / quarter-tile schedule)
     l1, g1, _ = handle.lml_grad_deriv_batched(t, yy, th[2:3], 1e-6)
-    assert l1[0] == lml[2] and np.array_equal(g1[0], grad[2])
+    assert abs(l1[0] - lml[2]) <= 1e-12 * abs(lml[2]) and relerr(g1[0], grad[2]) < 1e-11
 
 
 def test_headline_n4096_scale_and_homogeneity_properties(handle):

@@ -80,14 +80,15 @@ def test_rbf_cov_chol_through_the_shim(R):
     x = np.linspace(0, 10, 100)                       # test_interpolate.R:5-7 grid
     out = R.call("gp_rbf_cov_chol", x, 1.3)
     assert list(out) == ["L", "dLdl"]                 # covariance.cpp:41-46 names
-    Lr, dLr = o.rbf_cov_chol(x, 1.3)
-    S = o.rbf_gram_and_tangent(x, 1.3)[0]
-    assert np.max(np.abs(out["L"] @ out["L"].T - S)) < 1e-12
+    S, Sdot = o.rbf_gram_and_tangent(x, 1.3)
+    EPS = np.finfo(np.float64).eps
+    assert np.linalg.norm(out["L"] @ out["L"].T - S) / np.linalg.norm(S) < 50 * 100 * EPS
     assert np.all(np.triu(out["L"], 1) == 0) and np.all(np.triu(out["dLdl"], 1) == 0)
-    # jitter-only matrix: L itself is conditioning-limited, compare through the well-conditioned products
-    dS = out["dLdl"] @ out["L"].T + out["L"] @ out["dLdl"].T
-    dSr = dLr @ Lr.T + Lr @ dLr.T
-    assert np.max(np.abs(dS - dSr)) < 1e-8 * max(1.0, np.max(np.abs(dSr)))
+    # jitter-only matrix (cond ~ 1e10): assert the defining identity of the tangent, no worse than 10x the oracle
+    Lr, dLr = o.rbf_cov_chol(x, 1.3)
+    R = out["dLdl"] @ out["L"].T + out["L"] @ out["dLdl"].T - Sdot
+    Rr = dLr @ Lr.T + Lr @ dLr.T - Sdot
+    assert np.linalg.norm(R) <= 10 * max(np.linalg.norm(Rr), 1e-12 * np.linalg.norm(Sdot))
     # integer storage is coerced like Rcpp's NumericVector does
     xi = np.arange(12, dtype=np.int32)
     out2 = R.call("gp_rbf_cov_chol", xi, 2)
@@ -102,11 +103,11 @@ def test_cond_mvn_and_p_dotxn_matrix_through_the_shim(R):
     Xn = np.exp(tn) + 0.05 * rng.standard_normal(tn.shape[0])
     N = tn.shape[0]
     K = R.call("gp_gram_deriv", tn, 1.2, 0.9, 2, np.array([0.1, 0.0]), 1e-6, 1)
-    ref = o.p_dotXn(tn, Xn, (1.2, 0.9), 0.1, quirk=True)
+    rmean, rvar = o.p_dotXn(tn, Xn, (1.2, 0.9), 0.1, quirk=True)
     got = R.call("gp_cond_mvn", np.zeros(2 * N), K, N, Xn)
     assert list(got) == ["condMean", "condVar"]       # condMVNorm::condMVN names
-    assert np.max(np.abs(got["condMean"] - ref["condMean"])) < 1e-7 * np.max(np.abs(ref["condMean"]))
-    assert np.max(np.abs(got["condVar"] - ref["condVar"])) < 1e-7
+    assert np.max(np.abs(got["condMean"] - rmean)) < 1e-7 * np.max(np.abs(rmean))
+    assert np.max(np.abs(got["condVar"] - rvar)) < 1e-7
     got0 = R.call("gp_cond_mvn", None, K, N, Xn)      # mean = NULL means zeros
     assert np.array_equal(got0["condMean"], got["condMean"])
 
