@@ -39,6 +39,7 @@ SIGNATURES = {
     "gpb200_set_profiling": (C.c_int, [_h, C.c_int]),
     "gpb200_get_profile": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
     "gpb200_debug_bench_panel": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gpb200_debug_panel_trace": (C.c_int, [_h, C.c_void_p]),
     "gpb200_kernel_eval": (C.c_int, [_h, C.c_int, _ll, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     "gpb200_gram_outer": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                     C.c_void_p, C.c_int]),

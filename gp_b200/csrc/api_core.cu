@@ -46,9 +46,9 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   const char *tp = getenv("GPB200_TRSM_PIPELINED");
   if (tp && tp[0] == '0') h->trsm_pipelined = 0;
   const char *pv = getenv("GPB200_PANEL_V1");
-  if (pv && pv[0] == '1') h->panel_impl = 1;
+  if (pv && (pv[0] == '1' || pv[0] == '2')) h->panel_impl = pv[0] - '0';
   const char *tm = getenv("GPB200_TRSM_MT");
-  if (tm && (tm[0] == '1' || tm[0] == '2' || tm[0] == '4')) h->trsm_mt_override = tm[0] - '0';
+  if (tm && (tm[0] == '1' || tm[0] == '2')) h->trsm_mt_override = tm[0] - '0';
   const char *ng = getenv("GPB200_NO_GRAPH");
   if (ng && ng[0] == '1') h->graphs_enabled = 0;
   *out = h;
@@ -521,4 +521,11 @@ extern "C" int gpb200_debug_bench_panel(gpb200_handle_t h, int what, int nt, int
   if (rc) return rc;
   ms_out[0] = total / reps;
   return 0;
+}
+
+// instrumented builds only (-DGPB_PANEL_TRACE): clock64 stamps the panel kernels left for CTA 0 (tuning aid)
+extern "C" int gpb200_debug_panel_trace(gpb200_handle_t h, long long *out2048) {
+  CHECK_H(h);
+  GPB_CUDA(h, cudaDeviceSynchronize());
+  return panel_trace_fetch(out2048);
 }

@@ -64,7 +64,7 @@ struct Handle {
   int gemm_cfg_override = 0;  // 0 automatic, 1 one 128x128 CTA per SM, 2 two 128x64 half-tile CTAs per SM, 3 64x64 quarter-tile CTAs
   int quarter_below_waves = 2;  // automatic choice: quarter tiles while the half-tile grid is below this many waves of 2 x 148 CTAs
   int trsm_pipelined = 1;     // 0: one tile per CTA (the first TRSM tile kernel); env GPB200_TRSM_PIPELINED
-  int panel_impl = 0;         // 0: left-looking shared-memory panel kernels (round 2); 1: the round-1 register-tile kernels (env GPB200_PANEL_V1)
+  int panel_impl = 0;         // 0: round-2 shared-memory panel kernels (POTRF with a panel warp); 1: the round-1 register-tile kernels; 2: round-2 POTRF without the panel warp (env GPB200_PANEL_V1 = 1 | 2)
   int trsm_mt_override = 0;   // tuning knob: 8-row mma tiles per warp of trsm_ll_kernel (1, 2, 4); env GPB200_TRSM_MT
   char err[512] = {0};
   // grow-only device workspace
@@ -177,5 +177,6 @@ int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, l
 int launch_tile_inverse_at(Handle *h, const double *L, long long ld, long long l_off, long long l_step, double *W,
                            long long w_off, long long w_step, long long stride, int ntiles, int batch);
 int panel_smem_setup(Handle *h);
+int panel_trace_fetch(long long *out2048);  // instrumented builds (-DGPB_PANEL_TRACE) only
 
 }  // namespace gpb

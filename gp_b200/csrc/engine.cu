@@ -201,10 +201,13 @@ int chol_lookahead_panel(const Handle *h, int nt) {
 
 // Look-ahead schedule (small batches; one matrix does not fill the GPU and the panel chain of one POTRF tile and
 // one TRSM wave per block column is what bounds the factorisation):
-//   side stream P :  [in-panel left-looking update] -> POTRF -> TRSM   per block column of the panel
-//   main stream T :  wait(panel) -> update of the next panel's columns -> signal P -> update of the rest
-// so panel p+1 is factored while the bulk of panel p's trailing update still runs.  All writes to a block column
-// are ordered: its trailing updates happen on T in program order, and P touches it only after T's signal.
+//   side stream P :  [in-panel left-looking update] -> POTRF -> TRSM per block column, then the update of the NEXT
+//                    panel's columns by this panel (list 1) -- the whole dependent chain is consecutive launches of
+//                    ONE high-priority stream
+//   main stream T :  wait(panel p factored) -> update of everything right of the next panel (list 2)
+// so panel p+1 is factored while the bulk of panel p's trailing update still runs.  Every write to a block column
+// is ordered: before P updates the next panel's columns it waits for T's previous trailing update, which was the
+// last launch to write them; T's updates follow one another in stream order.
 static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev) {
   const int nt = np / TILE, pt = chol_lookahead_panel(h, nt);
   TaskList tl, tr, la1, la2;
@@ -225,6 +228,7 @@ static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int
   GPB_CUDA(h, cudaEventRecord(h->sync_event(ev), T));
   GPB_CUDA(h, cudaStreamWaitEvent(P, h->sync_event(ev), 0));
   ev++;
+  cudaEvent_t ev_trail = nullptr;  // T's most recent trailing update
   int panel = 0;
   for (int p0 = 0; p0 < nt; p0 += pt, panel++) {
     const int p1 = std::min(nt, p0 + pt);
@@ -237,23 +241,23 @@ static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int
       if ((rc = launch_potrf_tile(h, Lbuf, np, stride, j, n, batch, info_dev))) return rc;
       if ((rc = launch_trsm_tiles(h, Lbuf, np, stride, j, nt - 1 - j, batch))) return rc;
     }
-    GPB_CUDA(h, cudaEventRecord(h->sync_event(ev), P));
-    h->stream = T;
-    GPB_CUDA(h, cudaStreamWaitEvent(T, h->sync_event(ev), 0));
-    ev++;
+    cudaEvent_t ev_panel = h->sync_event(ev++);
+    GPB_CUDA(h, cudaEventRecord(ev_panel, P));
     if (p1 < nt) {
+      if (ev_trail) GPB_CUDA(h, cudaStreamWaitEvent(P, ev_trail, 0));
       p.tasks = la1.at(panel);
       if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, la1.count(panel), batch))) return rc;
-      GPB_CUDA(h, cudaEventRecord(h->sync_event(ev), T));
-      GPB_CUDA(h, cudaStreamWaitEvent(P, h->sync_event(ev), 0));
-      ev++;
-      if (la2.count(panel) > 0) {
-        p.tasks = la2.at(panel);
-        if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, la2.count(panel), batch))) return rc;
-      }
+    }
+    h->stream = T;
+    GPB_CUDA(h, cudaStreamWaitEvent(T, ev_panel, 0));
+    if (p1 < nt && la2.count(panel) > 0) {
+      p.tasks = la2.at(panel);
+      if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, la2.count(panel), batch))) return rc;
+      ev_trail = h->sync_event(ev++);
+      GPB_CUDA(h, cudaEventRecord(ev_trail, T));
     }
   }
-  return 0;  // T has waited for the last panel: the side stream is joined
+  return 0;  // T has waited for the last panel (which follows every launch on P): the side stream is joined
 }
 
 int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int batch, int *info_dev) {

@@ -9,6 +9,7 @@
 //                       rank-8 updates.  The same kernel with C = I and a transposed store
 //                       produces the inverse of a diagonal tile (seed of the recursive TRTRI).
 #include "common.cuh"
+#include "panel_ll.cuh"
 
 namespace gpb {
 
@@ -410,157 +411,201 @@ trsm_tiles_pipelined_kernel(const double *Ldiag_base, double *Cbase, long long l
 // ------------------------------------------------------------------------------------------------
 // Round-2 panel kernels: left-looking over 8-column blocks with the tile resident in SHARED memory.
 //
-// The round-1 kernels keep the 128x128 tile in registers in mma accumulator layout, which forces the
-// sixteen block steps to be fully unrolled (register arrays need static indices): potrf_tile_kernel_v2
-// is 28 000 SASS instructions, each executed once -- it runs at instruction-fetch speed (46 us per tile,
-// 5 600 cycles per block step against ~1 500 of dependent arithmetic).  With the tile in shared memory
-// every index is dynamic, the block loop stays rolled (a few hundred instructions), and the left-looking
-// order needs no register-resident trailing matrix at all:
+// The round-1 kernels keep the 128x128 tile in registers in mma accumulator layout, which forces the sixteen block
+// steps to be fully unrolled (register arrays need static indices): potrf_tile_kernel_v2 is 28 000 SASS instructions,
+// each executed once -- it runs at instruction-fetch speed (46 us per tile).  With the tile in shared memory every
+// index is dynamic, the block loop stays rolled, and the left-looking order needs no register-resident trailing matrix:
 //
 //   for cb = 0..15:   P  = T[:, 8cb:8cb+8] - T[:, 0:8cb] * T[8cb:8cb+8, 0:8cb]^T     DMMA, own rows
-//                     D  = chol(P[8cb:8cb+8, :])   every warp redundantly, in registers, no shuffles
-//                     T[below, 8cb:8cb+8] = P[below] D^-T    true substitution, one row per lane
+//                     D  = chol(P[8cb:8cb+8, :])                                     panel warp, in registers
+//                     T[below, 8cb:8cb+8] = P[below] D^-T                            true substitution, one row per lane
 //
-// potrf_tile_ll_kernel: two block barriers per step (the diagonal block must be complete before it is
-// factored; the solved panel must be visible before the next step's update).
-// trsm_ll_kernel: the rows of X = C L^-T are independent, so each warp runs its own rows through all
-// sixteen steps with no block barrier at all; a CTA takes 32, 64 or 128 rows so that a single large
-// matrix (batch 1) still spreads one block column over the whole GPU.
+// potrf_tile_pw_kernel  eight helper warps own the rows; a ninth PANEL WARP owns no rows and carries the serial chain
+//                       of the sixteen 8x8 diagonal blocks beside the helpers' DMMA work instead of in front of it:
+//                         phase 1  helpers substitute column block cb against D(cb)  | panel: partial sum of D(cb+1), k-blocks < cb
+//                         phase 2  helpers update column block cb+1 for their rows   | panel: last k-block, factor D(cb+1), publish
+// trsm_ll_kernel        the rows of X = C L^-T are independent: each warp runs its rows through all sixteen steps with
+//                       no block barrier; a CTA takes 32 or 64 rows so that ONE matrix spreads a block column over the GPU
+// tile_inverse_ll_kernel  X = L^-T row block by row block into the unused upper triangle of the staged tile
+// Per-phase cycle counts (tools/panel_trace.py, instrumented build) are in profiles/panel_trace_r02.txt.
 // ------------------------------------------------------------------------------------------------
 constexpr int LD_T = TILE + 4;  // column-major tile in shared memory, 132: conflict-free mma fragment reads
-constexpr int POTRF_LL_SMEM_BYTES = TILE * LD_T * (int)sizeof(double);
 
-// Cholesky of an 8x8 block held (lower part) in registers; every lane computes the same thing.
-// inv[k] = 1 / L[k][k]; bad = first k with a non-positive (or NaN) pivot, -1 if none.
-__device__ __forceinline__ void factor8_regs(double (&d)[8][8], double (&inv)[8], int &bad) {
-  bad = -1;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const double piv = d[k][k];
-    if (!(piv > 0.0) && bad < 0) bad = k;
-    const double r = rsqrt(piv);
-    inv[k] = r;
-    d[k][k] = piv * r;
-#pragma unroll
-    for (int i = k + 1; i < 8; i++) d[i][k] *= r;
-#pragma unroll
-    for (int j = k + 1; j < 8; j++)
-#pragma unroll
-      for (int i = j; i < 8; i++) d[i][j] = fma(-d[i][k], d[j][k], d[i][j]);
-  }
-}
+#ifdef GPB_PANEL_TRACE
+__device__ long long g_panel_trace[2048];
+#define PTRACE(cond, idx) do { if ((cond) && blockIdx.x == 0 && lane == 0) g_panel_trace[(idx)] = clock64(); } while (0)
+#else
+#define PTRACE(cond, idx) do { } while (0)
+#endif
+constexpr int POTRF_PW_THREADS = 288;
+constexpr int POTRF_PW_SMEM_BYTES = (TILE * LD_T + 16 * 64 + 16 * 8 + 64) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(256, 1)
-potrf_tile_ll_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
+__global__ void __launch_bounds__(POTRF_PW_THREADS, 1)
+potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
                      int n, int *info) {
   extern __shared__ __align__(16) double sm[];
-  double *Ts = sm;  // Ts[c * LD_T + r] = T[r][c]
-  __shared__ double Dsm[64];  // the updated diagonal block of the current step, Dsm[c * 8 + r]
+  double *Ts = sm;                    // Ts[c * LD_T + r] = T[r][c]  (rows at / below the 8-block of c only)
+  double *Dall = sm + TILE * LD_T;    // Dall[cb * 64 + c * 8 + cp] = L_D(cb)[c][cp], cp <= c (row-major), zero above
+  double *Iall = Dall + 16 * 64;      // Iall[cb * 8 + c] = 1 / L_D(cb)[c][c]
+  double *Dtmp = Iall + 16 * 8;       // the updated diagonal block on its way from mma layout to every lane
   __shared__ int s_info;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const bool panel = warp == 8;
   double *T = Lbase + (long long)blockIdx.x * stride + diag_off;
-  const int r0 = warp * 16;
   if (tid == 0) s_info = 0;
+  PTRACE(warp >= 7, (warp - 7) * 512 + 18 * 8 + 0);
 
-  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+  for (int idx = tid; idx < TILE * TILE / 2; idx += POTRF_PW_THREADS) {
     const int c = idx >> 6, r2 = idx & 63;
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(Ts + c * LD_T + 2 * r2);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(T + 2 * r2 + (long long)c * ld) : "memory");
+    if (2 * r2 + 1 >= (c & ~7)) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(Ts + c * LD_T + 2 * r2);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(T + 2 * r2 + (long long)c * ld) : "memory");
+    }
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
+  for (int idx = tid; idx < 16 * 64; idx += POTRF_PW_THREADS) Dall[idx] = 0.0;
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncthreads();
 
+  // factor the 8x8 block whose updated values sit in Dtmp[c * 8 + r] (column-major) and publish it as block `blk`
+  auto factor_publish = [&](int blk) {
+    double d[8][8], inv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int i = j; i < 8; i++) d[i][j] = Dtmp[j * 8 + i];
+    int bad;
+    factor8_pairs(d, inv, bad);
+    if (bad >= 0 && lane == 0 && s_info == 0) s_info = index_base + 8 * blk + bad + 1;
+    if (lane == 0) {  // every lane holds the same values: one writes the 36 + 8 results (the upper part stays zero)
+      double *o = Dall + blk * 64;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+#pragma unroll
+        for (int cp = 0; cp <= c; cp++) o[c * 8 + cp] = d[c][cp];
+        Iall[blk * 8 + c] = inv[c];
+      }
+    }
+  };
+
+  PTRACE(warp >= 7, (warp - 7) * 512 + 17 * 8 + 0);
+  if (panel) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) Dtmp[(2 * t + e) * 8 + g] = Ts[(2 * t + e) * LD_T + g];
+    __syncwarp();
+    factor_publish(0);
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  double ps[2][2];  // panel warp: running sum of L[c1.., k] L[c1.., k]^T for the NEXT diagonal block
 #pragma unroll 1
   for (int cb = 0; cb < 16; cb++) {
-    const int c0 = 8 * cb;
-    const bool active = (2 * warp + 1) >= cb;  // this warp still has rows at or below the diagonal block
-    // ---- 1. left-looking update of the warp's rows of block column cb -------------------------------
-    if (active && cb > 0) {
-      double s[2][2][2];
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-        for (int ch = 0; ch < 2; ch++) s[mt][ch][0] = s[mt][ch][1] = 0.0;
-      const bool m0 = (2 * warp) >= cb;  // the upper m-tile is still below / on the diagonal block
-      const double *pa = Ts + t * LD_T + r0 + g;
-      const double *pb = Ts + t * LD_T + c0 + g;
-      for (int kb = 0; kb < cb; kb++) {
-#pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-          const int ko = (8 * kb + 4 * ch) * LD_T;
-          const double b = pb[ko];
-          if (m0) dmma884p(s[0][ch], pa[ko], b);
-          dmma884p(s[1][ch], pa[ko + 8], b);
-        }
-      }
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-        if (mt == 0 && !m0) continue;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          double *p = Ts + (c0 + 2 * t + e) * LD_T + r0 + mt * 8 + g;
-          *p = (*p - s[mt][0][e]) - s[mt][1][e];
-        }
-      }
-    }
-    if (warp == (cb >> 1)) {
-      // publish the updated diagonal block apart from the tile: its rows are overwritten in place by their
-      // owner in step 2 while the other warps may still be reading it
-      __syncwarp();
-#pragma unroll
-      for (int e = 0; e < 2; e++) Dsm[(2 * t + e) * 8 + g] = Ts[(c0 + 2 * t + e) * LD_T + c0 + g];
-    }
-    __syncthreads();
-    // ---- 2. diagonal block (redundantly per lane) + substitution, one row per lane -------------------
-    if (active) {
-      double d[8][8], inv[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-#pragma unroll
-        for (int i = j; i < 8; i++) d[i][j] = Dsm[j * 8 + i];
-      int bad;
-      factor8_regs(d, inv, bad);
-      if (bad >= 0 && warp == (cb >> 1) && lane == 0 && s_info == 0) s_info = index_base + c0 + bad + 1;
+    const int c0 = 8 * cb, c1 = c0 + 8;
+    PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 0);
+    // ---- phase 1 ----------------------------------------------------------------------------------------------
+    if (!panel) {
       const int r = r0 + lane;
-      if (lane < 16 && r >= c0) {
-        double x[8];
+      if (lane < 16 && (r >> 3) > cb) {
+        double dl[8][8], inv[8], x[8];
+        double *px = Ts + c0 * LD_T + r;
 #pragma unroll
-        for (int c = 0; c < 8; c++) x[c] = Ts[(c0 + c) * LD_T + r];
+        for (int c = 0; c < 8; c++) x[c] = px[c * LD_T];
+        load_block8(Dall + cb * 64, Iall + cb * 8, dl, inv);
+        solve_row8(x, dl, inv);
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          double sv = x[c];
-#pragma unroll
-          for (int cp = 0; cp < c; cp++) sv = fma(-x[cp], d[c][cp], sv);
-          x[c] = sv * inv[c];
+        for (int c = 0; c < 8; c++) px[c * LD_T] = x[c];
+      }
+    } else if (cb < 15) {
+      ps[0][0] = ps[0][1] = ps[1][0] = ps[1][1] = 0.0;
+      if (cb > 0) {  // A and B fragments are the same registers: rows c1.. against themselves
+        const double *pa = Ts + t * LD_T + c1 + g;
+        double v0 = pa[0], v1 = pa[4 * LD_T];
+        for (int kb = 0; kb < cb; kb++) {
+          pa += 8 * LD_T;
+          double n0 = 0.0, n1 = 0.0;
+          if (kb + 1 < cb) { n0 = pa[0]; n1 = pa[4 * LD_T]; }
+          dmma884v(ps[0], v0, v0);
+          dmma884v(ps[1], v1, v1);
+          v0 = n0; v1 = n1;
         }
-        const int i = r - c0;  // < 8: a row of the diagonal block itself (the formula above reproduces L_D)
-#pragma unroll
-        for (int c = 0; c < 8; c++) Ts[(c0 + c) * LD_T + r] = (i < 8 && c > i) ? 0.0 : x[c];
       }
     }
+    PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 1);
     __syncthreads();
+    PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 2);
+    if (cb == 15) break;
+    // ---- phase 2 ----------------------------------------------------------------------------------------------
+    if (!panel) {
+      // each helper updates the rows it owns.  (Dealing the remaining row blocks out evenly over all eight helpers was
+      // measured SLOWER, 28.7 against 26.6 us per tile: the helpers are not the critical path, the panel warp is, and
+      // every extra busy warp takes issue slots and FP64-pipe cycles from it.)
+      const int rb0 = 2 * warp;
+      const bool act[2] = {rb0 > cb + 1, rb0 + 1 > cb + 1};
+      if (act[1]) {
+        double s[2][2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int ch = 0; ch < 2; ch++) s[mt][ch][0] = s[mt][ch][1] = 0.0;
+        ll_accumulate<2>(s, Ts + t * LD_T + 8 * rb0 + g, Ts + t * LD_T + c1 + g, cb + 1, 8 * LD_T, 8 * LD_T, 4 * LD_T, 4 * LD_T, 8, act);
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          if (!act[mt]) continue;
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            double *p = Ts + (c1 + 2 * t + e) * LD_T + 8 * (rb0 + mt) + g;
+            *p = (*p - s[mt][0][e]) - s[mt][1][e];
+          }
+        }
+      }
+    } else {
+      const double *pa = Ts + t * LD_T + c1 + g;
+      const double v0 = pa[c0 * LD_T], v1 = pa[(c0 + 4) * LD_T];
+      dmma884v(ps[0], v0, v0);
+      dmma884v(ps[1], v1, v1);
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+        Dtmp[(2 * t + e) * 8 + g] = (Ts[(c1 + 2 * t + e) * LD_T + c1 + g] - ps[0][e]) - ps[1][e];
+      __syncwarp();
+      PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 3);
+      factor_publish(cb + 1);
+    }
+    PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 4);
+    __syncthreads();
+    PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 5);
   }
+  PTRACE(warp >= 7, (warp - 7) * 512 + 16 * 8 + 0);
 
-  // write back: lower triangle = L, strict upper = 0 (Eigen matrixL() convention)
-  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+  // write back: lower triangle = L (diagonal blocks from Dall), strict upper = 0 (Eigen matrixL() convention)
+  for (int idx = tid; idx < TILE * TILE / 2; idx += POTRF_PW_THREADS) {
     const int c = idx >> 6, r = 2 * (idx & 63);
-    const double2 v = *reinterpret_cast<const double2 *>(Ts + c * LD_T + r);
-    *reinterpret_cast<double2 *>(T + r + (long long)c * ld) = make_double2(r >= c ? v.x : 0.0, r + 1 >= c ? v.y : 0.0);
+    double2 v = make_double2(0.0, 0.0);
+    if ((r >> 3) == (c >> 3)) {
+      const double *o = Dall + (c >> 3) * 64;
+      v.x = o[(r & 7) * 8 + (c & 7)];
+      v.y = o[((r + 1) & 7) * 8 + (c & 7)];
+    } else if (r > c) {
+      v = *reinterpret_cast<const double2 *>(Ts + c * LD_T + r);
+    }
+    *reinterpret_cast<double2 *>(T + r + (long long)c * ld) = v;
   }
+  PTRACE(warp >= 7, (warp - 7) * 512 + 16 * 8 + 1);
   if (tid == 0 && s_info != 0 && s_info <= n) {
     if (info[blockIdx.x] == 0) info[blockIdx.x] = s_info;
   }
 }
 
-// X L^T = C for ROWS = 32 MT consecutive rows of a block column (MODE-0 semantics of trsm_tile_kernel),
-// four warps of 8 MT rows each.  blockIdx.x = row chunk, blockIdx.y = batch item.
+// X L^T = C for ROWS = 32 MT consecutive rows of a block column (MODE-0 semantics of trsm_tile_kernel), four warps
+// of 8 MT rows each, no block barrier in the main loop.  blockIdx.x = row chunk, blockIdx.y = batch item.
+// The diagonal tile sits in shared memory as a full square (constant strides: every fragment address is one base
+// register plus an immediate), its sixteen 8x8 diagonal blocks once more row-major (Dall) for the substitution.
 template <int MT>
 struct TrsmLL {
   static constexpr int ROWS = 32 * MT;
   static constexpr int LD_C = ROWS + 4;
-  static constexpr int SMEM_BYTES = (LPK_DOUBLES + TILE + TILE * LD_C) * (int)sizeof(double);
+  static constexpr int SMEM_BYTES = (TILE * LD_T + 16 * 64 + TILE + TILE * LD_C) * (int)sizeof(double);
 };
 
 template <int MT>
@@ -568,9 +613,10 @@ __global__ void __launch_bounds__(128)
 trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long stride, long long diag_off, long long c_off) {
   constexpr int ROWS = TrsmLL<MT>::ROWS, LD_C = TrsmLL<MT>::LD_C;
   extern __shared__ __align__(16) double sm[];
-  double *Lp = sm;                  // packed lower triangle of the diagonal tile (see lpk_off / lpk_ld)
-  double *invd = sm + LPK_DOUBLES;  // 1 / L[n][n]
-  double *Cs = invd + TILE;         // Cs[c * LD_C + r] = C[r][c]
+  double *Ls = sm;                   // Ls[k * LD_T + n] = L[n][k]
+  double *Dall = sm + TILE * LD_T;   // Dall[cb * 64 + c * 8 + cp] = L[8cb + c][8cb + cp]
+  double *invd = Dall + 16 * 64;     // 1 / L[n][n]
+  double *Cs = invd + TILE;          // Cs[c * LD_C + r] = C[r][c]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const double *Ld = Ldiag_base + (long long)blockIdx.y * stride + diag_off;
@@ -580,13 +626,10 @@ trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long 
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
   };
-#pragma unroll 1
-  for (int cb = 0; cb < 16; cb++) {
-    const int rows2 = (TILE - 8 * cb) / 2;
-    for (int idx = tid; idx < 8 * rows2; idx += 128) {
-      const int kk = idx / rows2, r2 = idx - kk * rows2;
-      cp16(Lp + lpk_off(cb) + kk * lpk_ld(cb) + 2 * r2, Ld + (8 * cb + 2 * r2) + (long long)(8 * cb + kk) * ld);
-    }
+  PTRACE(warp == 0, 1024 + 18 * 8);
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 128) {
+    const int k = idx >> 6, r2 = idx & 63;
+    if (2 * r2 + 1 >= (k & ~7)) cp16(Ls + k * LD_T + 2 * r2, Ld + 2 * r2 + (long long)k * ld);  // rows at / below the block row of k
   }
   for (int idx = tid; idx < TILE * ROWS / 2; idx += 128) {
     const int c = idx / (ROWS / 2), r2 = idx - c * (ROWS / 2);
@@ -595,15 +638,24 @@ trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long 
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncthreads();
-  if (tid < TILE) invd[tid] = 1.0 / Lp[lpk_off(tid >> 3) + (tid & 7) * lpk_ld(tid >> 3) + (tid & 7)];
+  if (tid < TILE) invd[tid] = 1.0 / Ls[tid * LD_T + tid];
+  for (int idx = tid; idx < 16 * 64; idx += 128) {
+    const int cb = idx >> 6, c = (idx >> 3) & 7, cp = idx & 7;
+    Dall[idx] = Ls[(8 * cb + cp) * LD_T + 8 * cb + c];
+  }
   __syncthreads();
 
   const int r0 = warp * 8 * MT;
+  bool act[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++) act[mt] = true;
+  PTRACE(warp == 0, 1024 + 17 * 8);
 #pragma unroll 1
   for (int cb = 0; cb < 16; cb++) {
     const int c0 = 8 * cb;
-    const double *Lg = Lp + lpk_off(cb);
-    const int ldg = lpk_ld(cb);
+    PTRACE(warp == 0, 1024 + cb * 8 + 0);
+    double dl[8][8], inv[8];
+    load_block8(Dall + cb * 64, invd + c0, dl, inv);   // fetched before the DMMA loop: landed long before the substitution
     if (cb > 0) {
       // S = X[rows, 0:c0] * L[c0:c0+8, 0:c0]^T, two independent accumulation chains per m-tile
       double s[MT][2][2];
@@ -611,18 +663,7 @@ trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long 
       for (int mt = 0; mt < MT; mt++)
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) s[mt][ch][0] = s[mt][ch][1] = 0.0;
-      const double *pa = Cs + t * LD_C + r0 + g;
-      for (int kb = 0; kb < cb; kb++) {
-        const double *Lk = Lp + lpk_off(kb) + (c0 + g - 8 * kb);
-        const int ldk = lpk_ld(kb);
-#pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-          const double b = Lk[(4 * ch + t) * ldk];
-          const double *a = pa + (8 * kb + 4 * ch) * LD_C;
-#pragma unroll
-          for (int mt = 0; mt < MT; mt++) dmma884p(s[mt][ch], a[8 * mt], b);
-        }
-      }
+      ll_accumulate<MT>(s, Cs + t * LD_C + r0 + g, Ls + t * LD_T + c0 + g, cb, 8 * LD_C, 8 * LD_T, 4 * LD_C, 4 * LD_T, 8, act);
 #pragma unroll
       for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -632,39 +673,137 @@ trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long 
         }
       __syncwarp();
     }
+    PTRACE(warp == 0, 1024 + cb * 8 + 1);
     // substitution against the 8x8 diagonal block, one row per lane
     if (lane < 8 * MT) {
-      const int r = r0 + lane;
+      double *px = Cs + c0 * LD_C + r0 + lane;
       double x[8];
 #pragma unroll
-      for (int c = 0; c < 8; c++) x[c] = Cs[(c0 + c) * LD_C + r];
+      for (int c = 0; c < 8; c++) x[c] = px[c * LD_C];
+      solve_row8(x, dl, inv);
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        double sv = x[c];
-#pragma unroll
-        for (int cp = 0; cp < c; cp++) sv = fma(-x[cp], Lg[cp * ldg + c], sv);
-        x[c] = sv * invd[c0 + c];
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c++) Cs[(c0 + c) * LD_C + r] = x[c];
+      for (int c = 0; c < 8; c++) px[c * LD_C] = x[c];
     }
     __syncwarp();
+    PTRACE(warp == 0, 1024 + cb * 8 + 2);
   }
   __syncthreads();
+  PTRACE(warp == 0, 1024 + 16 * 8);
   for (int idx = tid; idx < TILE * ROWS / 2; idx += 128) {
     const int c = idx / (ROWS / 2), r2 = idx - c * (ROWS / 2);
     *reinterpret_cast<double2 *>(Ct + 2 * r2 + (long long)c * ld) = *reinterpret_cast<const double2 *>(Cs + c * LD_C + 2 * r2);
   }
 }
 
+// W = L^-1 of one 128x128 lower-triangular tile per CTA (MODE-1 semantics of trsm_tile_kernel: W lower triangular,
+// strict upper zero; in place allowed).  X = L^-T is computed row block by row block -- its rows are independent, so
+// the eight warps never meet at a barrier -- left-looking over the column blocks at and right of the row block
+// (everything left of it is zero and is skipped).  X is upper triangular and lives in the UNUSED upper triangle of
+// the staged L tile; its 8x8 diagonal blocks, which would collide with L's, go to a side buffer.  Warp w takes row
+// blocks w and 15 - w (a long and a short one).
+constexpr int TINV_SMEM_BYTES = (TILE * LD_T + 16 * 64 + TILE + 16 * 64) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+tile_inverse_ll_kernel(const double *Lbase, double *Wbase, long long ld, long long stride, long long l_off, long long l_step,
+                       long long w_off, long long w_step) {
+  extern __shared__ __align__(16) double sm[];
+  double *Ls = sm;                   // lower: Ls[k * LD_T + n] = L[n][k]; strict upper (outside diagonal blocks): X[r][c] at Ls[c * LD_T + r]
+  double *Dall = sm + TILE * LD_T;   // Dall[cb * 64 + c * 8 + cp] = L[8cb + c][8cb + cp]
+  double *invd = Dall + 16 * 64;     // 1 / L[n][n] = X[n][n]
+  double *XD = invd + TILE;          // XD[rb * 64 + k * 8 + i] = X[8rb + i][8rb + k]  (upper triangular incl. diagonal)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double *Ld = Lbase + (long long)blockIdx.y * stride + l_off + (long long)blockIdx.x * l_step;
+  double *Wt = Wbase + (long long)blockIdx.y * stride + w_off + (long long)blockIdx.x * w_step;
+
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+    const int k = idx >> 6, r2 = idx & 63;
+    if (2 * r2 + 1 >= (k & ~7)) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(Ls + k * LD_T + 2 * r2);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ld + 2 * r2 + (long long)k * ld) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  if (tid < TILE) invd[tid] = 1.0 / Ls[tid * LD_T + tid];
+  for (int idx = tid; idx < 16 * 64; idx += 256) {
+    const int cb = idx >> 6, c = (idx >> 3) & 7, cp = idx & 7;
+    Dall[idx] = Ls[(8 * cb + cp) * LD_T + 8 * cb + c];
+  }
+  __syncthreads();
+
+  const bool act[1] = {true};
+#pragma unroll 1
+  for (int slot = 0; slot < 2; slot++) {
+    const int rb = slot == 0 ? warp : 15 - warp;
+    const int r0 = 8 * rb;
+    double *xd = XD + rb * 64;
+#pragma unroll 1
+    for (int cb = rb; cb < 16; cb++) {
+      const int c0 = 8 * cb;
+      double dl[8][8], inv[8];
+      load_block8(Dall + cb * 64, invd + c0, dl, inv);
+      if (cb > rb) {
+        double s[1][2][2];
+        s[0][0][0] = s[0][0][1] = s[0][1][0] = s[0][1][1] = 0.0;
+        const double *pb = Ls + t * LD_T + c0 + g;
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) dmma884v(s[0][ch], xd[(4 * ch + t) * 8 + g], pb[(r0 + 4 * ch) * LD_T]);   // k-block rb: the diagonal block of X
+        ll_accumulate<1>(s, Ls + t * LD_T + r0 + g + (r0 + 8) * LD_T, pb + (r0 + 8) * LD_T, cb - rb - 1, 8 * LD_T, 8 * LD_T, 4 * LD_T,
+                         4 * LD_T, 0, act);
+#pragma unroll
+        for (int e = 0; e < 2; e++) Ls[(c0 + 2 * t + e) * LD_T + r0 + g] = -(s[0][0][e] + s[0][1][e]);
+        __syncwarp();
+      }
+      if (lane < 8) {
+        const int i = lane, r = r0 + i;
+        double x[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) x[c] = (cb == rb) ? ((c == i) ? 1.0 : 0.0) : Ls[(c0 + c) * LD_T + r];
+        solve_row8(x, dl, inv);
+        if (cb == rb) {
+#pragma unroll
+          for (int c = 0; c < 8; c++) xd[c * 8 + i] = (c >= i) ? x[c] : 0.0;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; c++) Ls[(c0 + c) * LD_T + r] = x[c];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // W[c][r] = X[r][c] for c >= r, zero above: column r of W is row r of X
+  for (int idx = tid; idx < TILE * TILE / 2; idx += 256) {
+    const int r = idx >> 6, c = 2 * (idx & 63);
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int cc = c + e;
+      v[e] = (cc < r) ? 0.0 : (((cc >> 3) == (r >> 3)) ? XD[(r >> 3) * 64 + (cc & 7) * 8 + (r & 7)] : Ls[cc * LD_T + r]);
+    }
+    *reinterpret_cast<double2 *>(Wt + c + (long long)r * ld) = make_double2(v[0], v[1]);
+  }
+}
+
+int panel_trace_fetch(long long *out2048) {
+#ifdef GPB_PANEL_TRACE
+  return cudaMemcpyFromSymbol(out2048, g_panel_trace, sizeof(long long) * 2048) == cudaSuccess ? 0 : -1000;
+#else
+  (void)out2048;
+  return -1;
+#endif
+}
+
 int panel_smem_setup(Handle *h) {
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tiles_pipelined_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_PIPE_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(potrf_tile_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_LL_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(tile_inverse_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TINV_SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(potrf_tile_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_PW_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<1>::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<2>::SMEM_BYTES));
-  GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<4>::SMEM_BYTES));
   return 0;
 }
 
@@ -674,7 +813,7 @@ int launch_potrf_tile_at(Handle *h, double *L, long long ld, long long stride, l
   if (h->panel_impl == 1)
     potrf_tile_kernel_v2<<<batch, 256, 0, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
   else
-    potrf_tile_ll_kernel<<<batch, 256, POTRF_LL_SMEM_BYTES, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
+    potrf_tile_pw_kernel<<<batch, POTRF_PW_THREADS, POTRF_PW_SMEM_BYTES, h->stream>>>(L, ld, stride, diag_off, index_base, n, info);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
@@ -690,8 +829,18 @@ int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, l
   if (ntiles <= 0) return 0;
   const long long total = (long long)ntiles * batch;
   ProfScope ps__(h, PC_TRSM);
-  if (h->panel_impl == 1) {
-    // round-1 kernels: tiles per CTA as many as still leave every SM several CTAs
+  // Few tiles (one large matrix, batch 1..2: the latency path): the row-split left-looking kernel, 32 or 64 rows per
+  // CTA, so that one block column covers the GPU in a single wave.  Otherwise the DMMA-throughput kernels of round 1:
+  // one tile per CTA, or several row tiles per CTA pipelined when there are many.
+  int mt = h->trsm_mt_override;
+  if (mt != 1 && mt != 2) mt = (h->panel_impl == 1) ? 0 : (total * 4 <= 148 ? 1 : (total * 2 <= 148 ? 2 : 0));
+  if (mt == 1) {
+    dim3 grid(ntiles * 4, batch);
+    trsm_ll_kernel<1><<<grid, 128, TrsmLL<1>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
+  } else if (mt == 2) {
+    dim3 grid(ntiles * 2, batch);
+    trsm_ll_kernel<2><<<grid, 128, TrsmLL<2>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
+  } else {
     const int tpc = total >= 148 * 16 ? 4 : (total >= 148 * 6 ? 2 : 1);
     if (tpc == 1 || h->trsm_pipelined == 0) {
       dim3 grid(ntiles, batch);
@@ -700,14 +849,6 @@ int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, l
       dim3 grid((ntiles + tpc - 1) / tpc, batch);
       trsm_tiles_pipelined_kernel<2><<<grid, 256, TRSM_PIPE_SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off, ntiles, tpc);
     }
-  } else {
-    // rows per CTA: 32 while that still fits one wave of two CTAs per SM (a single large matrix), else 128
-    int mt = h->trsm_mt_override;
-    if (mt != 1 && mt != 2 && mt != 4) mt = (total * 4 <= 2 * 148) ? 1 : ((total * 2 <= 148) ? 2 : 4);
-    dim3 grid(ntiles * (4 / mt), batch);
-    if (mt == 1) trsm_ll_kernel<1><<<grid, 128, TrsmLL<1>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
-    else if (mt == 2) trsm_ll_kernel<2><<<grid, 128, TrsmLL<2>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
-    else trsm_ll_kernel<4><<<grid, 128, TrsmLL<4>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
   }
   GPB_LAUNCH_CHECK(h);
   return 0;
@@ -723,7 +864,8 @@ int launch_tile_inverse_at(Handle *h, const double *L, long long ld, long long l
                            long long w_off, long long w_step, long long stride, int ntiles, int batch) {
   dim3 grid(ntiles, batch);
   ProfScope ps__(h, PC_TRSM);
-  trsm_tile_kernel<1><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, W, ld, stride, l_off, l_step, w_off, w_step);
+  if (h->panel_impl == 1) trsm_tile_kernel<1><<<grid, 256, TRSM_SMEM_BYTES, h->stream>>>(L, W, ld, stride, l_off, l_step, w_off, w_step);
+  else tile_inverse_ll_kernel<<<grid, 256, TINV_SMEM_BYTES, h->stream>>>(L, W, ld, stride, l_off, l_step, w_off, w_step);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }

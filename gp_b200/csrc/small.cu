@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "fastexp.cuh"
 #include "gram.cuh"
+#include "panel_ll.cuh"
 
 namespace gpb {
 
@@ -32,25 +33,6 @@ __device__ __forceinline__ double warp_sum_s(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-// Cholesky of an 8x8 block held (lower part) in registers; every lane computes the same thing.
-__device__ __forceinline__ void factor8_small(double (&d)[8][8], double (&inv)[8], int &bad) {
-  bad = -1;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const double piv = d[k][k];
-    if (!(piv > 0.0) && bad < 0) bad = k;
-    const double r = rsqrt(piv);
-    inv[k] = r;
-    d[k][k] = piv * r;
-#pragma unroll
-    for (int i = k + 1; i < 8; i++) d[i][k] *= r;
-#pragma unroll
-    for (int j = k + 1; j < 8; j++)
-#pragma unroll
-      for (int i = j; i < 8; i++) d[i][j] = fma(-d[i][k], d[j][k], d[i][j]);
-  }
 }
 
 __global__ void __launch_bounds__(256, 2)
@@ -147,7 +129,7 @@ lml_small_kernel(int n, int n8, const double *__restrict__ x, long long x_stride
 #pragma unroll
           for (int i = j; i < 8; i++) d[i][j] = Dsm[j * 8 + i];
         int bad;
-        factor8_small(d, inv, bad);
+        factor8_pairs(d, inv, bad);
         if (bad >= 0 && warp == (cb & 7) && lane == 0 && s_info == 0) s_info = c0 + bad + 1;
         if (lane < 16 && rb >= cb && rb < nb) {
           const int r = 8 * rb + (lane & 7);

@@ -86,9 +86,9 @@ def test_rbf_cov_chol_through_the_shim(R):
     assert np.all(np.triu(out["L"], 1) == 0) and np.all(np.triu(out["dLdl"], 1) == 0)
     # jitter-only matrix (cond ~ 1e10): assert the defining identity of the tangent, no worse than 10x the oracle
     Lr, dLr = o.rbf_cov_chol(x, 1.3)
-    R = out["dLdl"] @ out["L"].T + out["L"] @ out["dLdl"].T - Sdot
+    Res = out["dLdl"] @ out["L"].T + out["L"] @ out["dLdl"].T - Sdot
     Rr = dLr @ Lr.T + Lr @ dLr.T - Sdot
-    assert np.linalg.norm(R) <= 10 * max(np.linalg.norm(Rr), 1e-12 * np.linalg.norm(Sdot))
+    assert np.linalg.norm(Res) <= 10 * max(np.linalg.norm(Rr), 1e-12 * np.linalg.norm(Sdot))
     # integer storage is coerced like Rcpp's NumericVector does
     xi = np.arange(12, dtype=np.int32)
     out2 = R.call("gp_rbf_cov_chol", xi, 2)

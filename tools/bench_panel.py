@@ -11,11 +11,14 @@ sys.path.insert(0, ".")
 
 def run_variant():
     from gp_b200 import capi
+    label_skip_inverse = os.environ.get("GPB200_TRSM_MT") is not None
     h = capi.Handle(0)
     out = {}
     for what, name in ((0, "potrf_tile"), (1, "trsm_tiles"), (2, "tile_inverse")):
-        for nt, batch in ((32, 1), (16, 1), (8, 1), (32, 4), (8, 32), (32, 128)):
+        for nt, batch in ((32, 1), (8, 1), (32, 2), (32, 4), (8, 32), (32, 128)):
             if what == 0 and nt != 32:
+                continue
+            if what == 2 and label_skip_inverse:
                 continue
             out["%s nt=%d B=%d" % (name, nt, batch)] = round(h.debug_bench_panel(what, nt, batch, 5) * 1e3, 2)
     print(json.dumps(out))
@@ -26,8 +29,8 @@ if __name__ == "__main__":
         run_variant()
         sys.exit(0)
     res = {}
-    for label, env in (("round2_ll", {}), ("round1_v1", {"GPB200_PANEL_V1": "1"}),
-                       ("ll_mt1", {"GPB200_TRSM_MT": "1"}), ("ll_mt2", {"GPB200_TRSM_MT": "2"}), ("ll_mt4", {"GPB200_TRSM_MT": "4"})):
+    for label, env in (("round2_panel_warp", {}), ("round1_v1", {"GPB200_PANEL_V1": "1"}),
+                       ("ll_mt1", {"GPB200_TRSM_MT": "1"}), ("ll_mt2", {"GPB200_TRSM_MT": "2"})):
         e = dict(os.environ); e.update(env)
         r = subprocess.run([sys.executable, __file__, "child"], env=e, capture_output=True, text=True)
         if r.returncode != 0:
