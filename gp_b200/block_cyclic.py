@@ -22,6 +22,7 @@ buffers, collectives) can be exercised with world_size-2 gloo processes on CPU
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import numpy as np
@@ -83,11 +84,76 @@ class GpuPanelBackend:
     def to_host(self, t):
         return t.cpu().numpy()
 
+    # -- collectives enqueued from C (ncclBroadcast / ncclAllReduce on the handle's streams) -------------
+    def init_comm(self, group=None):
+        """Creates the handle's NCCL communicator: rank 0 draws the unique id in C (gpb200_mg_comm_id), the
+        128 bytes travel once through torch.distributed, every rank calls gpb200_mg_comm_init."""
+        import torch.distributed as dist
+        torch = self.torch
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if world > 1:
+            if rank == 0:
+                buf = (C.c_char * 128)()
+                self._chk(self.lib.gpb200_mg_comm_id(self.h._h, buf), "mg_comm_id")
+                ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            ident = ident.to(self.device)
+            dist.broadcast(ident, src=0, group=group)
+            ident = ident.cpu()
+        raw = (C.c_char * 128).from_buffer_copy(bytes(ident.numpy().tobytes()))
+        self._chk(self.lib.gpb200_mg_comm_init(self.h._h, raw, rank, world), "mg_comm_init")
+        self.native_comm = True
+        return self
+
+    def close_comm(self):
+        if getattr(self, "native_comm", False):
+            self.lib.gpb200_mg_comm_destroy(self.h._h)
+            self.native_comm = False
+
+    def bcast(self, buf, count, root):
+        t = C.c_longlong(0)
+        self._chk(self.lib.gpb200_mg_bcast(self.h._h, buf.data_ptr(), int(count), int(root), C.byref(t)), "mg_bcast")
+        return t.value
+
+    def wait(self, ticket):
+        self._chk(self.lib.gpb200_mg_wait(self.h._h, int(ticket)), "mg_wait")
+
+    def allreduce(self, t, op="sum"):
+        is_int = t.dtype == self.torch.int32
+        self._chk(self.lib.gpb200_mg_allreduce(self.h._h, t.data_ptr(), t.numel(), 1 if op == "max" else 0, int(is_int)),
+                  "mg_allreduce")
+
+    # -- distributed gradient building blocks ---------------------------------------------------------------
+    def my_columns(self, n, pc, rank, world):
+        return int(self.lib.gpb200_mg_my_columns(n, pc, rank, world))
+
+    def panel_to_square(self, n, col0, ncols, P, ldp, Lsq):
+        self._chk(self.lib.gpb200_mg_panel_to_square(self.h._h, n, col0, ncols, P.data_ptr(), ldp, Lsq.data_ptr()),
+                  "mg_panel_to_square")
+
+    def inverse_rows(self, n, pc, rank, world, Lsq, Xp, S, Wd):
+        self._chk(self.lib.gpb200_mg_inverse_rows(self.h._h, n, pc, rank, world, Lsq.data_ptr(), Xp.data_ptr(), S.data_ptr(),
+                                                  Wd.data_ptr()), "mg_inverse_rows")
+
+    def solve_partials(self, n, pc, rank, world, Lsq, Xp, ypad, z_mine, a_part, sums2, part):
+        self._chk(self.lib.gpb200_mg_solve_partials(self.h._h, n, pc, rank, world, Lsq.data_ptr(), Xp.data_ptr(), ypad.data_ptr(),
+                                                    z_mine.data_ptr(), a_part.data_ptr(), sums2.data_ptr(), part.data_ptr()),
+                  "mg_solve_partials")
+
+    def quadform_partials(self, n, rank, world, x, a, theta3, part, sums2):
+        self._chk(self.lib.gpb200_mg_quadform_partials(self.h._h, n, rank, world, x.data_ptr(), a.data_ptr(), theta3.data_ptr(),
+                                                       part.data_ptr(), sums2.data_ptr()), "mg_quadform_partials")
+
+    def trace_partials(self, n, pc, rank, world, Xp, x, avec, theta3, partial, sums3):
+        self._chk(self.lib.gpb200_mg_trace_partials(self.h._h, n, pc, rank, world, Xp.data_ptr(), x.data_ptr(), avec.data_ptr(),
+                                                    theta3.data_ptr(), partial.data_ptr(), sums3.data_ptr()), "mg_trace_partials")
+
 
 class BlockCyclicGP:
     """Distributed factorisation and LML of one exact GP with a squared-exponential kernel."""
 
-    def __init__(self, n, panel_cols=512, backend=None, group=None):
+    def __init__(self, n, panel_cols=512, backend=None, group=None, keep_all=False):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -102,6 +168,13 @@ class BlockCyclicGP:
         self.be = backend
         self.panels = {}
         self.info = None
+        # keep_all: every rank keeps every broadcast panel (the gradient needs the whole factor on every rank; the
+        # panels arrive anyway).  Otherwise two receive buffers are recycled.
+        self.keep_all = bool(keep_all)
+        self.received = {}
+        self.native = bool(getattr(backend, "native_comm", False))
+        self.x_dev = None
+        self.theta = None
 
     # -- geometry -----------------------------------------------------------------------------
     def owner(self, p):
@@ -122,15 +195,32 @@ class BlockCyclicGP:
     def _bcast(self, tensor, src, async_op=False):
         if self.world == 1:
             return None
+        if self.native:   # enqueued from C on the handle's communication stream; the "work" is a ticket
+            ticket = self.be.bcast(tensor, tensor.numel(), src)
+            if async_op:
+                return ticket
+            self.be.wait(ticket)
+            return None
         return self.dist.broadcast(tensor, src=src, group=self.group, async_op=async_op)
+
+    def _wait(self, work):
+        if work is None:
+            return
+        if self.native:
+            self.be.wait(work)
+        else:
+            work.wait()
 
     # -- factorisation ------------------------------------------------------------------------
     def factor(self, x, alpha, rho, sigma, jitter=0.0):
         """K = cov_exp_quad(x, alpha, rho) + (sigma^2 + jitter) I  ->  L, distributed.  Returns LAPACK info."""
         be, n = self.be, self.n
         dx = be.from_host(x)
+        self.x_dev = dx
+        self.theta = (float(alpha), float(rho), float(sigma), float(jitter))
         self.info = be.info_scalar()
         self.panels = {}
+        self.received = {}
         for p in self.my_panels():
             P = be.empty(self.ld(p), self.ncols(p))
             be.gram_panel(n, dx, float(alpha), float(rho), float(sigma) ** 2 + float(jitter), self.col0(p),
@@ -144,6 +234,9 @@ class BlockCyclicGP:
             own = self.owner(p)
             if own == self.rank:
                 buf = self.panels[p]
+            elif self.keep_all:
+                buf = be.empty(self.ld(p), self.ncols(p))
+                self.received[p] = buf
             else:
                 slot = p % 2
                 need = self.ld(p) * self.ncols(p)
@@ -158,8 +251,7 @@ class BlockCyclicGP:
         start_bcast(0)
         for p in range(self.npanels):
             buf, work = pending.pop(p)
-            if work is not None:
-                work.wait()
+            self._wait(work)
             nxt = p + 1
             if nxt < self.npanels:
                 if self.owner(nxt) == self.rank:
@@ -176,9 +268,59 @@ class BlockCyclicGP:
             # first failing pivot over all ranks: max over ranks of (info>0 ? BIG - info : 0) keeps the smallest
             big = 1 << 30
             enc = (info > 0).to(info.dtype) * (big - info)
-            self.dist.all_reduce(enc, op=self.dist.ReduceOp.MAX, group=self.group)
+            if self.native:
+                self.be.allreduce(enc, "max")
+            else:
+                self.dist.all_reduce(enc, op=self.dist.ReduceOp.MAX, group=self.group)
             info = (enc > 0).to(info.dtype) * (big - enc)
         return int(be.to_host(info)[0])
+
+    # -- likelihood AND gradient ---------------------------------------------------------------------
+    def lml_grad(self, y):
+        """MVN(y | 0, K) log density and its gradient in (alpha, rho, sigma) (models/fit_hyperparameters.stan:19-31 and
+        its reverse sweep) from the distributed factor.  Needs keep_all=True (every rank holds every panel).  Exact:
+        rank r inverts the rows of L^-1 that belong to its panels and contracts K^-1's contribution of those rows with
+        dK/dtheta in the fused trace epilogue; two small all-reduces combine the ranks.  No stochastic estimator."""
+        if not self.keep_all:
+            raise ValueError("lml_grad needs BlockCyclicGP(..., keep_all=True)")
+        be, n, np_, pc = self.be, self.n, self.np_, self.pc
+        torch = be.torch
+        alpha, rho, sigma, _ = self.theta
+        Lsq = be.empty(np_, np_)
+        for p in range(self.npanels):
+            P = self.panels[p] if self.owner(p) == self.rank else self.received[p]
+            be.panel_to_square(n, self.col0(p), self.ncols(p), P, self.ld(p), Lsq)
+        nmine = be.my_columns(n, pc, self.rank, self.world)
+        Xp = be.empty(np_, max(nmine, 1))
+        S = be.empty(pc, max(nmine, 1))
+        Wd = be.empty(pc * pc, 2 * self.npanels)
+        ypad = be.from_host(np.concatenate([np.asarray(y, dtype=np.float64), np.zeros(np_ - n)]))
+        z_mine = be.vector(max(nmine, 1))
+        a = be.vector(np_)
+        sums2 = be.vector(2)
+        part = be.vector(8 * np_, zero=False)
+        be.inverse_rows(n, pc, self.rank, self.world, Lsq, Xp, S, Wd)
+        be.solve_partials(n, pc, self.rank, self.world, Lsq, Xp, ypad, z_mine, a, sums2, part)
+        del S, Wd, Lsq
+        qf = sums2[0:1].clone()
+        if self.world > 1:
+            be.allreduce(a)
+            be.allreduce(qf)
+        nt = np_ // TILE
+        partial = be.vector(16 * nt * (nt + 1) // 2, zero=False)
+        sums5 = be.vector(5)    # (-sum G e, -sum G e d^2, tr G) of this rank's rows of L^-1, then (a^T E a, a^T (E o D2) a) of its slice
+        theta3 = be.from_host(np.array([alpha, rho, sigma]))
+        be.trace_partials(n, pc, self.rank, self.world, Xp, self.x_dev, be.vector(np_), theta3, partial, sums5[0:3])
+        be.quadform_partials(n, self.rank, self.world, self.x_dev, a, theta3, partial, sums5[3:5])
+        if self.world > 1:
+            be.allreduce(sums5)
+        aa = float((a[:n] * a[:n]).sum().item())
+        s5 = be.to_host(sums5)
+        s_se, s_d2, s_tr = float(s5[0] + s5[3]), float(s5[1] + s5[4]), float(s5[2])
+        logdet = float(be.to_host(sums2)[1])
+        lml = -0.5 * n * math.log(2.0 * math.pi) - logdet - 0.5 * float(qf.item())
+        grad = np.array([alpha * s_se, 0.5 * alpha * alpha * s_d2 / rho ** 3, sigma * (aa - s_tr)])
+        return lml, grad
 
     # -- likelihood ---------------------------------------------------------------------------
     def lml(self, y):

@@ -84,6 +84,20 @@ SIGNATURES = {
                                          _ll]),
     "gpb200_mg_panel_trsv": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
+    "gpb200_mg_comm_id": (C.c_int, [_h, C.c_void_p]),
+    "gpb200_mg_comm_init": (C.c_int, [_h, C.c_void_p, C.c_int, C.c_int]),
+    "gpb200_mg_comm_destroy": (C.c_int, [_h]),
+    "gpb200_mg_bcast": (C.c_int, [_h, C.c_void_p, _ll, C.c_int, C.POINTER(_ll)]),
+    "gpb200_mg_wait": (C.c_int, [_h, _ll]),
+    "gpb200_mg_allreduce": (C.c_int, [_h, C.c_void_p, _ll, C.c_int, C.c_int]),
+    "gpb200_mg_panel_to_square": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p]),
+    "gpb200_mg_my_columns": (_ll, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gpb200_mg_inverse_rows": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpb200_mg_solve_partials": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpb200_mg_trace_partials": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
+    "gpb200_mg_quadform_partials": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpb200_mg_panel_logdiag": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p]),
 }
 

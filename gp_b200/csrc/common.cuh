@@ -85,6 +85,13 @@ struct Handle {
   // a high-priority side stream while the rest of the trailing update runs on the handle's stream
   cudaStream_t pstream = nullptr;
   std::vector<cudaEvent_t> sync_events;
+  // config 5: NCCL communicator owned by the handle (loaded at run time, api_mg.cu), its own stream and a ring of
+  // events that order collectives against the compute stream
+  void *nccl_comm = nullptr;
+  int mg_rank = 0, mg_world = 1;
+  cudaStream_t cstream = nullptr;
+  std::vector<cudaEvent_t> mg_events;
+  long long mg_tickets = 0;
   int small_kernel = 1;         // one-CTA whole-evaluation kernel for n <= 128 (env GPB200_SMALL_KERNEL=0 disables)
   int lookahead = 1;            // env GPB200_LOOKAHEAD=0 disables
   int lookahead_max_batch = 8;  // batches up to this size take the look-ahead schedule

@@ -430,6 +430,7 @@ static int smem_setup_cfg(Handle *h) {
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, false, false, EPI_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<Cfg, true, true, EPI_TRACE_DERIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   return 0;
 }
@@ -454,6 +455,8 @@ static int launch_cfg(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParam
   } else if (layout == LAYOUT_TN) {
     if (epi == EPI_TRACE_DERIV) return launch_one<Cfg, true, true, EPI_TRACE_DERIV>(h, p, ntasks, batch);
     return launch_one<Cfg, true, true, EPI_TRACE>(h, p, ntasks, batch);
+  } else if (layout == LAYOUT_NT && epi == EPI_TRACE) {
+    return launch_one<Cfg, false, false, EPI_TRACE>(h, p, ntasks, batch);  // G = X X^T of the distributed gradient (api_mg.cu)
   }
   snprintf(h->err, sizeof(h->err), "launch_gemm: unsupported layout/epilogue %d/%d", (int)layout, (int)epi);
   return -2;

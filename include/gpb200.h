@@ -245,6 +245,45 @@ GPB200_API int gpb200_mg_panel_trsv(gpb200_handle_t h, int n, int col0, int ncol
 GPB200_API int gpb200_mg_panel_logdiag(gpb200_handle_t h, int n, int col0, int ncols, const double *P,
                                        long long ldp, double *out);
 
+
+/* ---- (e) collectives of config 5, enqueued from C.  NCCL is loaded at run time (the copy the host process
+ * already carries, e.g. torch's, else the system libnccl.so.2; GPB200_NCCL_LIB overrides).  The communicator lives in
+ * the handle: rank 0 draws the 128-byte unique id, the caller ships it to the other ranks by whatever means it has
+ * (torch.distributed, MPI, a file), every rank calls comm_init.  gpb200_mg_bcast runs ncclBroadcast on the handle's
+ * own communication stream, ordered behind the compute stream by an event, and returns a ticket; gpb200_mg_wait makes
+ * the compute stream wait for that ticket -- so a panel travels over NVLink while the trailing update runs. */
+GPB200_API int gpb200_mg_comm_id(gpb200_handle_t h, void *id128);
+GPB200_API int gpb200_mg_comm_init(gpb200_handle_t h, const void *id128, int rank, int world);
+GPB200_API int gpb200_mg_comm_destroy(gpb200_handle_t h);
+GPB200_API int gpb200_mg_bcast(gpb200_handle_t h, double *buf, long long count, int root, long long *ticket);
+GPB200_API int gpb200_mg_wait(gpb200_handle_t h, long long ticket);
+/* in-place all-reduce on the compute stream: op 0 sum, 1 max; is_int != 0 for int32 data */
+GPB200_API int gpb200_mg_allreduce(gpb200_handle_t h, void *buf, long long count, int op, int is_int);
+
+/* ---- (e) distributed GRADIENT of config 5: per-rank building blocks without communication (DEVICE pointers).
+ * Every rank holds the whole factor after the factorisation (its panels and the broadcast copies).  Rank r computes
+ * the columns of X = L^-T of ITS panels (= its rows of L^-1; N^3/3P flops), z_k = x_k^T y for its k, a_r = X_r z_r, and
+ * feeds G_r = X_r X_r^T tile by tile to the fused trace epilogue (N^3/3P flops): since tr(K^-1 dK) = sum_k w_k dK w_k^T
+ * over the rows w_k of L^-1, the partial sums of the ranks add up to the single-GPU result exactly.
+ *   Lsq np x np (ld np): full lower factor; Xp np x nmine (ld np): the rank's columns of X, packed;
+ *   S pc x nmine and Wd 2 * npanels * pc * pc doubles: scratch; nmine = gpb200_mg_my_columns(...). */
+GPB200_API int gpb200_mg_panel_to_square(gpb200_handle_t h, int n, int col0, int ncols, const double *P, long long ldp, double *Lsq);
+GPB200_API long long gpb200_mg_my_columns(int n, int pc, int rank, int world);
+GPB200_API int gpb200_mg_inverse_rows(gpb200_handle_t h, int n, int pc, int rank, int world, const double *Lsq, double *Xp,
+                                      double *S, double *Wd);
+/* z_mine = X_r^T y, sums2 = (sum z_mine^2, log det L), a_part = X_r z_mine; ypad = y padded with zeros to np; part: 8 np scratch */
+GPB200_API int gpb200_mg_solve_partials(gpb200_handle_t h, int n, int pc, int rank, int world, const double *Lsq, const double *Xp,
+                                        const double *ypad, double *z_mine, double *a_part, double *sums2, double *part);
+/* sums3 = (sum M e, sum M e d^2, tr G_r) over the tiles this rank's columns reach, M = avec avec^T - G_r.  Pass a ZERO
+ * avec for the distributed gradient (the a a^T half comes from gpb200_mg_quadform_partials, which covers every tile);
+ * theta3 = device (alpha, rho, sigma); partial: 16 * nt (nt + 1) / 2 doubles of scratch, nt = np / 128 */
+GPB200_API int gpb200_mg_trace_partials(gpb200_handle_t h, int n, int pc, int rank, int world, const double *Xp, const double *x,
+                                        const double *avec, const double *theta3, double *partial, double *sums3);
+/* sums2 = (a^T E a, a^T (E o D^2) a) over this rank's contiguous share of the rows, E_ij = exp(-(x_i - x_j)^2 / 2 rho^2);
+ * part: 2 * ceil(n / 128) doubles of scratch */
+GPB200_API int gpb200_mg_quadform_partials(gpb200_handle_t h, int n, int rank, int world, const double *x, const double *a,
+                                           const double *theta3, double *part, double *sums2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,7 @@ def test_sass_is_sm100a_dmma():
     # split per function and look at the NT instance of the tile GEMM
     chunks = sass.split("Function : ")
     gemm = [c for c in chunks if c.startswith("_ZN3gpb16gemm_tile_kernel")]
-    assert len(gemm) == 18         # three configurations x (NT, TN, NN, TT, TN + SE trace, TN + derivative trace)
+    assert len(gemm) == 21         # three configurations x (NT, TN, NN, TT, TN + SE trace, TN + derivative trace, NT + SE trace)
     for c in gemm:
         assert c.count("DMMA.8x8x4") >= 64 and "LDGSTS" in c
     # no library GEMM/solver is linked: the O(N^3) work is ours
