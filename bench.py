@@ -162,6 +162,39 @@ def measure_latency(h, dev, stream, reps=20):
     return out
 
 
+def measure_block_cyclic(h, dev, world, rank, sizes=(32768, 16384, 8192)):
+    """Config 5: ONE large exact GP, LML + gradient (models/fit_hyperparameters.stan:19-31 semantics), factor
+    block-column-cyclic over the ranks with the panel broadcasts enqueued from C (gpb200_mg_bcast -> ncclBroadcast), exact
+    distributed gradient.  Time = factorisation + gradient, CUDA events, max over ranks, best of 2 after a warm-up."""
+    import importlib.util
+    import numpy as np
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_block_cyclic", os.path.join(ROOT, "tools", "bench_block_cyclic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from gp_b200.block_cyclic import GpuPanelBackend
+    be = GpuPanelBackend(h, dev).init_comm()
+    out = {}
+    try:
+        for n in sizes:
+            pc = 256 if n // world <= 2048 else 512   # narrower panels when each rank holds few of them (measured: 8 ranks, N = 16 384)
+            rec, (x, y, theta) = mod.run_one(n, pc, be, h, dev, world, rank, reps=2)
+            rec.pop("grad", None)
+            if rank == 0 and n <= 8192:   # checker leg: the oracle at a size it finishes in seconds
+                from oracle import gp_oracle as _o
+                from threadpoolctl import threadpool_limits
+                with threadpool_limits(limits=os.cpu_count() or 1):
+                    rv, rg = _o.lml_grad_lapack(x, y, *theta)
+                rec["relerr_lml_vs_oracle"] = float(abs(rec["lml"] - rv) / abs(rv))
+                rec["relerr_grad_vs_oracle"] = float(np.max(np.abs(np.asarray(rec["grad_full"]) - rg)) / np.max(np.abs(rg)))
+            rec.pop("grad_full", None)
+            out["n%d" % n] = rec
+    finally:
+        be.close_comm()
+        h.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    return out
+
+
 def cpu_reference_evals_per_sec(n_evals, threads):
     """Times the CPU oracle (LAPACK route) on `n_evals` draws of the N=4096 workload with `threads`
     BLAS threads (torchrun exports OMP_NUM_THREADS=1, so the pool size is set explicitly)."""
@@ -407,6 +440,12 @@ def main():
                                 "substitution), N^3/3 flops per evaluation, CUDA events, max over ranks"}
 
     line["parity"] = parity
+    if world > 1:
+        bc = measure_block_cyclic(h, dev, world, rank)
+        if rank == 0:
+            line["block_cyclic"] = dict(bc, what="config 5: one exact GP of size N, LML+gradient, block-column-cyclic Cholesky with "
+                                                 "NCCL panel broadcasts enqueued from C + exact distributed gradient; frac = N^3 / time / "
+                                                 "(n_gpus x measured FP64 peak)")
     if latency is not None:
         if world == 1 and not args.no_cpu_baseline:   # the small latency cases are checked against the oracle too
             for k, rec in latency.items():

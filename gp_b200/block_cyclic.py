@@ -69,6 +69,13 @@ class GpuPanelBackend:
         self._chk(self.lib.gpb200_mg_panel_factor(self.h._h, n, col0, ncols, P.data_ptr(), ldp, info.data_ptr()),
                   "mg_panel_factor")
 
+    def panel_factor_col(self, n, col0, ncols, P, ldp, jl, info):
+        self._chk(self.lib.gpb200_mg_panel_factor_col(self.h._h, n, col0, ncols, P.data_ptr(), ldp, jl, info.data_ptr()),
+                  "mg_panel_factor_col")
+
+    def use_stream(self, stream):
+        self.h.set_stream(stream.cuda_stream)
+
     def panel_update(self, n, pcol0, pncols, P, ldp, ccol0, cncols, Cp, ldc):
         self._chk(self.lib.gpb200_mg_panel_update(self.h._h, n, pcol0, pncols, P.data_ptr(), ldp, ccol0, cncols,
                                                   Cp.data_ptr(), ldc), "mg_panel_update")
@@ -221,6 +228,8 @@ class BlockCyclicGP:
         self.info = be.info_scalar()
         self.panels = {}
         self.received = {}
+        if self.native:
+            return self._factor_native(dx, alpha, rho, sigma, jitter)
         for p in self.my_panels():
             P = be.empty(self.ld(p), self.ncols(p))
             be.gram_panel(n, dx, float(alpha), float(rho), float(sigma) ** 2 + float(jitter), self.col0(p),
@@ -272,6 +281,104 @@ class BlockCyclicGP:
                 self.be.allreduce(enc, "max")
             else:
                 self.dist.all_reduce(enc, op=self.dist.ReduceOp.MAX, group=self.group)
+            info = (enc > 0).to(info.dtype) * (big - enc)
+        return int(be.to_host(info)[0])
+
+    def _factor_native(self, dx, alpha, rho, sigma, jitter):
+        """The same right-looking schedule with everything enqueued from C and nothing waiting on the host:
+          * the panel chain -- apply panel p to panel p+1, factor it tile column by tile column, hand each finished
+            tile column to ncclBroadcast -- runs on a HIGH-PRIORITY stream, so it overtakes the rank's own backlog of
+            trailing updates (on the main stream) instead of queueing behind it;
+          * a tile column travels while the next one is being factored (four broadcasts of ldp x 128 per 512-panel);
+          * every rank waits for a panel only where it first reads it."""
+        be, n = self.be, self.n
+        torch = be.torch
+        main = torch.cuda.current_stream(be.device)
+        if getattr(self, "_pstream", None) is None:
+            self._pstream = torch.cuda.Stream(device=be.device, priority=-1)
+        ps = self._pstream
+        be.use_stream(main)
+        for p in self.my_panels():
+            P = be.empty(self.ld(p), self.ncols(p))
+            be.gram_panel(n, dx, float(alpha), float(rho), float(sigma) ** 2 + float(jitter), self.col0(p), self.ncols(p), P,
+                          self.ld(p))
+            self.panels[p] = P
+        recv = [None, None]
+        last_ticket = [None]
+        last_upd = {}          # my panel q -> event after the latest trailing update written into it (main stream)
+        built = torch.cuda.Event()
+        built.record(main)
+
+        def buffer_of(p):
+            if self.owner(p) == self.rank:
+                return self.panels[p]
+            if self.keep_all:
+                self.received[p] = be.empty(self.ld(p), self.ncols(p))
+                return self.received[p]
+            slot = p % 2
+            need = self.ld(p) * self.ncols(p)
+            if recv[slot] is None or recv[slot].numel() < need:
+                recv[slot] = be.empty(self.ld(0), self.pc)
+            return recv[slot].reshape(-1)[:need].reshape(self.ncols(p), self.ld(p))
+
+        def factor_and_bcast(p, prev_buf, prev_tickets):
+            """panel stream: (apply panel p-1) -> factor tile columns -> broadcast each; returns (buffer, tickets)"""
+            own = self.owner(p)
+            buf = buffer_of(p)
+            ntc = self.ncols(p) // TILE
+            chunk = self.ld(p) * TILE
+            flat = buf.reshape(-1)
+            tickets = []
+            be.use_stream(ps)
+            if own == self.rank:
+                ps.wait_event(last_upd.get(p, built))
+                if prev_buf is not None:
+                    for t in prev_tickets:
+                        be.wait(t)
+                    be.panel_update(n, self.col0(p - 1), self.ncols(p - 1), prev_buf, self.ld(p - 1), self.col0(p), self.ncols(p),
+                                    buf, self.ld(p))
+            elif not self.keep_all:
+                # a recycled receive buffer may still be read by trailing updates of panel p-2 on the main stream
+                ev = torch.cuda.Event(); ev.record(main); ps.wait_event(ev)
+            for jl in range(ntc):
+                if own == self.rank:
+                    be.panel_factor_col(n, self.col0(p), self.ncols(p), buf, self.ld(p), jl, self.info)
+                tickets.append(be.bcast(flat[jl * chunk:(jl + 1) * chunk], chunk, own))
+            last_ticket[0] = tickets[-1]
+            be.use_stream(main)
+            return buf, tickets
+
+        cur_buf, cur_t = factor_and_bcast(0, None, None)
+        for p in range(self.npanels):
+            nxt = p + 1
+            nxt_buf = nxt_t = None
+            if nxt < self.npanels:
+                nxt_buf, nxt_t = factor_and_bcast(nxt, cur_buf, cur_t)
+            be.use_stream(main)
+            mine = [q for q in self.my_panels() if q > nxt]
+            if mine:
+                for t in cur_t:
+                    be.wait(t)
+                for q in mine:
+                    be.panel_update(n, self.col0(p), self.ncols(p), cur_buf, self.ld(p), self.col0(q), self.ncols(q),
+                                    self.panels[q], self.ld(q))
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    last_upd[q] = ev
+            cur_buf, cur_t = nxt_buf, nxt_t
+        done = torch.cuda.Event()
+        done.record(ps)
+        main.wait_event(done)
+        # every broadcast has to have landed before anyone reads the received panels (the communication stream runs
+        # them in order: waiting for the last ticket covers all)
+        be.use_stream(main)
+        if last_ticket[0] is not None:
+            be.wait(last_ticket[0])
+        info = self.info.clone()
+        if self.world > 1:
+            big = 1 << 30
+            enc = (info > 0).to(info.dtype) * (big - info)
+            be.allreduce(enc, "max")
             info = (enc > 0).to(info.dtype) * (big - enc)
         return int(be.to_host(info)[0])
 

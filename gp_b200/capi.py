@@ -80,6 +80,7 @@ SIGNATURES = {
     "gpb200_mg_gram_panel": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, _ll]),
     "gpb200_mg_panel_factor": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p]),
+    "gpb200_mg_panel_factor_col": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_int, C.c_void_p]),
     "gpb200_mg_panel_update": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_int, C.c_int, C.c_void_p,
                                          _ll]),
     "gpb200_mg_panel_trsv": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, C.c_void_p,

@@ -170,41 +170,58 @@ extern "C" int gpb200_mg_gram_panel(gpb200_handle_t h, int n, const double *x, d
   return launch_gram_se_panel(h, n, np, x, alpha, rho, diag_add, col0, ncols, P, ldp);
 }
 
-extern "C" int gpb200_mg_panel_factor(gpb200_handle_t h, int n, int col0, int ncols, double *P, long long ldp,
-                                      int *info_dev) {
-  CHECK_H(h);
-  int np;
-  RC(mg_check_panel(h, n, col0, ncols, ldp, &np));
+namespace {
+// one tile column jl of the in-panel left-looking factorisation: update with the panel's columns to its left, POTRF, TRSM
+int mg_factor_col(Handle *h, int n, int col0, int ncols, double *P, long long ldp, int jl, int *info_dev) {
+  const int np = round_up(n, TILE);
   const int ntp = ncols / TILE, nrt = (np - col0) / TILE;
   TaskList tl;
   const long long key = mgkey(TK_MG_FACTOR, nrt, ntp, 0, 0);
   if (!cached(h, key, &tl)) {
     std::vector<TileTask> t;
     std::vector<int> off(1, 0);
-    for (int jl = 0; jl < ntp; jl++) {
-      if (jl > 0)
-        for (int i = jl; i < nrt; i++) t.push_back({i * TILE, 0, jl * TILE, 0, i * TILE, jl * TILE, jl * TILE, i == jl});
+    for (int j = 0; j < ntp; j++) {
+      if (j > 0)
+        for (int i = j; i < nrt; i++) t.push_back({i * TILE, 0, j * TILE, 0, i * TILE, j * TILE, j * TILE, i == j});
       off.push_back((int)t.size());
     }
     RC(upload_tasks(h, key, t, off, &tl));
   }
-  GemmParams p{};
-  p.A = mref(P, ldp, 0);
-  p.B = mref(P, ldp, 0);
-  p.C = mref(P, ldp, 0);
-  p.C0 = mref(P, ldp, 0);
-  p.alpha = -1.0;
-  p.beta = 1.0;
-  for (int jl = 0; jl < ntp; jl++) {
-    if (tl.count(jl) > 0) {
-      p.tasks = tl.at(jl);
-      RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(jl), 1));
-    }
-    const long long doff = (long long)jl * TILE * (ldp + 1);
-    RC(launch_potrf_tile_at(h, P, ldp, 0, doff, col0 + jl * TILE, n, 1, info_dev));
-    RC(launch_trsm_tiles_at(h, P, ldp, 0, doff, doff + TILE, nrt - 1 - jl, 1));
+  if (tl.count(jl) > 0) {
+    GemmParams p{};
+    p.A = mref(P, ldp, 0);
+    p.B = mref(P, ldp, 0);
+    p.C = mref(P, ldp, 0);
+    p.C0 = mref(P, ldp, 0);
+    p.alpha = -1.0;
+    p.beta = 1.0;
+    p.tasks = tl.at(jl);
+    RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(jl), 1));
   }
+  const long long doff = (long long)jl * TILE * (ldp + 1);
+  RC(launch_potrf_tile_at(h, P, ldp, 0, doff, col0 + jl * TILE, n, 1, info_dev));
+  return launch_trsm_tiles_at(h, P, ldp, 0, doff, doff + TILE, nrt - 1 - jl, 1);
+}
+}  // namespace
+
+extern "C" int gpb200_mg_panel_factor(gpb200_handle_t h, int n, int col0, int ncols, double *P, long long ldp,
+                                      int *info_dev) {
+  CHECK_H(h);
+  int np;
+  RC(mg_check_panel(h, n, col0, ncols, ldp, &np));
+  for (int jl = 0; jl < ncols / TILE; jl++) RC(mg_factor_col(h, n, col0, ncols, P, ldp, jl, info_dev));
   return 0;
+}
+
+// The same, one 128-wide tile column at a time (jl = 0 .. ncols/128 - 1, in order): a finished tile column can be
+// handed to gpb200_mg_bcast while the next one is still being factored.
+extern "C" int gpb200_mg_panel_factor_col(gpb200_handle_t h, int n, int col0, int ncols, double *P, long long ldp, int jl,
+                                          int *info_dev) {
+  CHECK_H(h);
+  int np;
+  RC(mg_check_panel(h, n, col0, ncols, ldp, &np));
+  if (jl < 0 || jl >= ncols / TILE) BAD_ARG(h, 7, "mg_panel_factor_col: tile column outside the panel");
+  return mg_factor_col(h, n, col0, ncols, P, ldp, jl, info_dev);
 }
 
 extern "C" int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P, long long ldp,
@@ -302,12 +319,21 @@ extern "C" int gpb200_mg_panel_logdiag(gpb200_handle_t h, int n, int col0, int n
 namespace {
 enum { TK_MG_XSOLVE = 42, TK_MG_XUPDATE = 43, TK_MG_XTRACE = 44 };
 
+// Which columns of X a rank computes is free (every rank holds all of L): panels are dealt out in SNAKE order
+// (0..P-1, P-1..0, 0..P-1, ...) because the cost of a column panel grows with the square of its index -- the plain
+// cyclic deal of the factorisation gives the last rank 39 % more inverse work than the first at 8 ranks x 64 panels.
+__host__ __device__ inline int mg_snake_panel(int q, int rank, int world) { return q * world + ((q & 1) ? world - 1 - rank : rank); }
+
 struct MgGeom {
   int np, pc, npanels, rank, world, nq;
   long long nmine;
   int ncols(int p) const { return std::min(pc, np - p * pc); }
-  int panel_of(int q) const { return rank + q * world; }
-  int first_q_at_or_after(int P) const { return P <= rank ? 0 : (P - rank + world - 1) / world; }
+  int panel_of(int q) const { return mg_snake_panel(q, rank, world); }
+  int first_q_at_or_after(int P) const {   // smallest q with panel_of(q) >= P (panel_of is increasing in q)
+    int q = P / world;
+    if (panel_of(q) < P) q++;
+    return q;
+  }
 };
 
 int mg_geom(Handle *h, int n, int pc, int rank, int world, MgGeom *g) {
@@ -319,7 +345,7 @@ int mg_geom(Handle *h, int n, int pc, int rank, int world, MgGeom *g) {
   g->world = world;
   g->nq = 0;
   g->nmine = 0;
-  for (int p = rank; p < g->npanels; p += world) { g->nq++; g->nmine += g->ncols(p); }
+  for (int q = 0; g->panel_of(q) < g->npanels; q++) { g->nq++; g->nmine += g->ncols(g->panel_of(q)); }
   return 0;
 }
 
@@ -329,7 +355,7 @@ __global__ void mg_x_init_kernel(int np, int pc, int rank, int world, long long 
     const long long kk = e / np;
     const int i = (int)(e - kk * np);
     const int q = (int)(kk / pc);
-    const long long gcol = (long long)(rank + q * world) * pc + (kk - (long long)q * pc);
+    const long long gcol = (long long)mg_snake_panel(q, rank, world) * pc + (kk - (long long)q * pc);
     Xp[e] = (i == gcol) ? 1.0 : 0.0;
   }
 }

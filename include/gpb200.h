@@ -234,6 +234,10 @@ GPB200_API int gpb200_mg_gram_panel(gpb200_handle_t h, int n, const double *x, d
 /* Cholesky of the (already updated) panel in place: diagonal block + everything below it */
 GPB200_API int gpb200_mg_panel_factor(gpb200_handle_t h, int n, int col0, int ncols, double *P, long long ldp,
                                       int *info_dev);
+/* the same, one 128-wide tile column at a time (jl = 0 .. ncols/128 - 1, in order), so that a finished tile column
+ * can travel (gpb200_mg_bcast of its ldp * 128 doubles) while the next one is being factored */
+GPB200_API int gpb200_mg_panel_factor_col(gpb200_handle_t h, int n, int col0, int ncols, double *P, long long ldp, int jl,
+                                          int *info_dev);
 /* right-looking update of a panel to the right: C -= P(rows of C) P(cols of C)^T, lower part */
 GPB200_API int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P,
                                       long long ldp, int ccol0, int cncols, double *C, long long ldc);
