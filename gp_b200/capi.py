@@ -66,6 +66,9 @@ SIGNATURES = {
                                               C.c_void_p]),
     "gpb200_se_chol_tangent": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
                                          C.c_void_p, C.c_void_p]),
+    "gpb200_latent_forward": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    "gpb200_latent_backward": (C.c_int, [_h, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpb200_approx_L": (C.c_int, [_h, C.c_int, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p), C.c_void_p]),
     "gpb200_approx_Lz": (C.c_int, [_h, C.c_int, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
@@ -408,6 +411,26 @@ class Handle:
         self._check(self.lib.gpb200_se_chol_tangent(self._h, n, _ptr(x), alpha, rho, diag_add, int(wrt), _ptr(L),
                                                     _ptr(dL)), "se_chol_tangent")
         return L, dL
+
+    def latent_forward(self, x, alpha, rho, diag_add, z):
+        """f = L z (z: (n,) or (nvec, n)) with L = chol(cov_exp_quad(x, alpha, rho) + diag_add I); L stays on the device."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        z2 = np.ascontiguousarray(np.atleast_2d(np.asarray(z, dtype=np.float64)))
+        n, nvec = x.shape[0], z2.shape[0]
+        f = np.empty((nvec, n))
+        self._check(self.lib.gpb200_latent_forward(self._h, n, _ptr(x), alpha, rho, diag_add, nvec, _ptr(z2), _ptr(f)), "latent_forward")
+        return f[0] if np.ndim(z) == 1 else f
+
+    def latent_backward(self, x, alpha, rho, diag_add, z, fbar):
+        """Reverse sweep through f = L z and the Cholesky: returns ((d/dalpha, d/drho), zbar)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        z2 = np.ascontiguousarray(np.atleast_2d(np.asarray(z, dtype=np.float64)))
+        fb = np.ascontiguousarray(np.atleast_2d(np.asarray(fbar, dtype=np.float64)))
+        n, nvec = x.shape[0], z2.shape[0]
+        tb = np.empty(2); zbar = np.empty((nvec, n))
+        self._check(self.lib.gpb200_latent_backward(self._h, n, _ptr(x), alpha, rho, diag_add, nvec, _ptr(z2), _ptr(fb), _ptr(tb),
+                                                    _ptr(zbar)), "latent_backward")
+        return tb, (zbar[0] if np.ndim(z) == 1 else zbar)
 
     def _tables(self, Ls, dLdls):
         Ls = [_f(a) for a in Ls]; dLs = [_f(a) for a in dLdls]

@@ -67,6 +67,7 @@ extern "C" int gpb200_destroy(gpb200_handle_t h) {
   if (h->g_in) cudaEventDestroy(h->g_in);
   if (h->g_out) cudaEventDestroy(h->g_out);
   if (h->ws) cudaFree(h->ws);
+  if (h->latent_L) cudaFree(h->latent_L);
   for (auto &kv : h->task_cache) cudaFree(kv.second.first);
   delete h;
   return 0;

@@ -30,7 +30,8 @@ enum { TF_DIAG = 1,
        TF_A_TRI_FIRST = 2,   // first k-tile of A is zero where k_local < m_local
        TF_A_TRI_LAST = 4,    // last  k-tile of A is zero where k_local > m_local
        TF_B_TRI_FIRST = 8,   // first k-tile of B is zero where k_local < n_local
-       TF_B_TRI_LAST = 16 }; // last  k-tile of B is zero where k_local > n_local
+       TF_B_TRI_LAST = 16,   // last  k-tile of B is zero where k_local > n_local
+       TF_FULL_WEIGHT = 32 };// trace epilogue: the tile is NOT half of a symmetric pair (weight 1; reverse-mode adjoint)
 
 struct MatRef {
   double *p;
@@ -92,6 +93,12 @@ struct Handle {
   cudaStream_t cstream = nullptr;
   std::vector<cudaEvent_t> mg_events;
   long long mg_tickets = 0;
+  // factor kept between gpb200_latent_forward and gpb200_latent_backward (api_latent.cu)
+  double *latent_L = nullptr;
+  size_t latent_bytes = 0;
+  double latent_key[4] = {0, 0, 0, 0};
+  int latent_n = 0;
+  unsigned long long latent_xhash = 0;
   int small_kernel = 1;         // one-CTA whole-evaluation kernel for n <= 128 (env GPB200_SMALL_KERNEL=0 disables)
   int lookahead = 1;            // env GPB200_LOOKAHEAD=0 disables
   int lookahead_max_batch = 8;  // batches up to this size take the look-ahead schedule

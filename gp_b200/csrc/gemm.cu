@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
         }
       }
     }
-    const double w = (diag_tile && (Cfg::NSPLIT_M == 1 || m0 == n0)) ? 1.0 : 2.0;  // a diagonal quadrant / full diagonal tile holds both (i,j) and (j,i)
+    const double w = ((task.flags & TF_FULL_WEIGHT) || (diag_tile && (Cfg::NSPLIT_M == 1 || m0 == n0))) ? 1.0 : 2.0;  // a diagonal quadrant / full diagonal tile holds both (i,j) and (j,i)
     s_k *= w;
     s_dk *= w;
 #pragma unroll
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::MINB) gemm_tile_kernel(con
         }
       }
     }
-    const double w = (diag_tile && (Cfg::NSPLIT_M == 1 || m0 == n0)) ? 1.0 : 2.0;  // a diagonal quadrant / full diagonal tile holds both (i,j) and (j,i)
+    const double w = ((task.flags & TF_FULL_WEIGHT) || (diag_tile && (Cfg::NSPLIT_M == 1 || m0 == n0))) ? 1.0 : 2.0;  // a diagonal quadrant / full diagonal tile holds both (i,j) and (j,i)
     s_se *= w;
     s_d2 *= w;
 #pragma unroll

@@ -185,6 +185,17 @@ GPB200_API int gpb200_rbf_cov_chol_batched(gpb200_handle_t h, int n, const doubl
 GPB200_API int gpb200_se_chol_tangent(gpb200_handle_t h, int n, const double *x, double alpha, double rho,
                                       double diag_add, int wrt, double *L, double *dL);
 
+/* f-2, REVERSE mode: the non-centred latent models differentiate through cholesky_decompose (exact_gp.stan:17-25,
+ * fit_full_gp.stan:18-26, westbrook_exact.stan:17-24; heteroscedastic.stan:23-32 with two mat-vecs on one L).
+ * forward: f_m = L z_m, m < nvec, L = chol(cov_exp_quad(x, alpha, rho) + diag_add I) (kept on the device);
+ * backward: given fbar_m = d lp / d f_m, zbar_m = L^T fbar_m and theta_bar = d lp / d (alpha, rho) through f and the
+ * Cholesky (Kbar = L^-T Phi(L^T Lbar) L^-1 contracted with dK/dtheta): ONE N^3 pass for all parameters, instead of one
+ * 5 N^3 / 3 forward-mode pass per parameter.  z, f, fbar, zbar: nvec consecutive vectors of length n. */
+GPB200_API int gpb200_latent_forward(gpb200_handle_t h, int n, const double *x, double alpha, double rho, double diag_add,
+                                     int nvec, const double *z, double *f);
+GPB200_API int gpb200_latent_backward(gpb200_handle_t h, int n, const double *x, double alpha, double rho, double diag_add,
+                                      int nvec, const double *z, const double *fbar, double *theta_bar, double *zbar);
+
 /* approx_L (covariance.cpp:49-96): cubic-Hermite interpolation in l between tabulated factors;
  * Ls / dLdls are P pointers to n x n column-major tables, lp the P grid points. */
 GPB200_API int gpb200_approx_L(gpb200_handle_t h, int n, double l, int P, const double *lp,

@@ -128,6 +128,44 @@ def test_latent_exact_gp_gradient_through_cholesky(handle):
     assert relerr(L, o.cholesky_decompose(o.gram_se(x, 1.3, 0.9, 1e-6))) < 1e-9
 
 
+@pytest.mark.parametrize("n", [60, 200, 700])
+def test_reverse_mode_cholesky_adjoint_matches_oracle_and_forward_mode(handle, n):
+    """f-2: gpb200_latent_forward / _backward (ONE pass of the Cholesky adjoint for all parameters) against the oracle's
+    NumPy reverse sweep, against the round-1 forward-mode route, and -- for alpha, which the oracle does not differentiate --
+    against central differences of the oracle's lp; then heteroscedastic.stan:23-32's two mat-vecs on one L (nvec = 2)."""
+    from gp_b200 import latent_gp
+    rng = np.random.default_rng(n)
+    x = np.arange(n) * 0.8 + 0.05 * rng.standard_normal(n)
+    y = np.sin(x) + 0.1 * rng.standard_normal(n)
+    z = rng.standard_normal(n)
+    lp, g = latent_gp.exact_gp_log_prob(x, y, 0.9, 0.3, z, handle=handle, reverse=True)
+    lpf, gf = latent_gp.exact_gp_log_prob(x, y, 0.9, 0.3, z, handle=handle, reverse=False)
+    rlp, rg = o.exact_gp_lp_grad(x, y, 0.9, 0.3, z)
+    assert abs(lp - rlp) <= 1e-9 * abs(rlp) and abs(lp - lpf) <= 1e-12 * abs(lp)
+    assert abs(g["l"] - rg["l"]) <= 1e-8 * abs(rg["l"]) and abs(g["l"] - gf["l"]) <= 1e-8 * abs(gf["l"])
+    assert relerr(g["z"], rg["z"]) < 1e-9 and relerr(g["f"], rg["f"]) < 1e-9
+    # amplitude (fit_full_gp.stan:18-26, jitter 1e-6 keeps the finite difference meaningful)
+    a0, l0, jit = 1.3, 0.9, 1e-6
+
+    def lp_of(alpha):
+        L = o.cholesky_decompose(o.gram_se(x, alpha, l0, jit))
+        r = y - L @ z
+        return -0.5 * float(r @ r) / 0.3 ** 2
+    f = handle.latent_forward(x, a0, l0, jit, z)
+    fbar = (y - f) / 0.3 ** 2
+    (ga, gl), zbar = handle.latent_backward(x, a0, l0, jit, z, fbar)
+    hh = 1e-6
+    assert abs(ga - (lp_of(a0 + hh) - lp_of(a0 - hh)) / (2 * hh)) <= 2e-6 * max(1.0, abs(ga))
+    L = o.cholesky_decompose(o.gram_se(x, a0, l0, jit))
+    assert relerr(zbar, L.T @ fbar) < 1e-9 and relerr(f, L @ z) < 1e-9
+    # two mat-vecs on one factor: the adjoints add
+    z2 = rng.standard_normal(n); fb2 = rng.standard_normal(n)
+    (ga1, gl1), _ = handle.latent_backward(x, a0, l0, jit, z2, fb2)
+    (gab, glb), zb = handle.latent_backward(x, a0, l0, jit, np.stack([z, z2]), np.stack([fbar, fb2]))
+    assert abs(gab - (ga + ga1)) <= 1e-9 * max(abs(ga), abs(ga1)) and abs(glb - (gl + gl1)) <= 1e-9 * max(abs(gl), abs(gl1))
+    assert relerr(zb[1], L.T @ fb2) < 1e-9
+
+
 def test_create_p_dotXnS_sequential_sampler(handle):
     # R/tests.R:78-99 shape: condition on data, then query new states one at a time
     from gp_b200 import ode_gp_library as lib
