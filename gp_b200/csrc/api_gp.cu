@@ -250,12 +250,12 @@ int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, const 
   const size_t mat = (size_t)np * np;
   const long long st = (long long)mat;
   Arena a;
-  RC(ws_reserve(h, 4 * P * pad256(mat * 8) + pad256(n * 8) + pad256((size_t)n * n * 8) + pad256(P * 8) + pad256(P * 4) + 2048, &a));
+  RC(ws_reserve(h, 4 * P * pad256(mat * 8) + pad256(n * 8) + (h->device_ptrs ? 0 : pad256((size_t)2 * P * n * n * 8)) + pad256(P * 8) + pad256(P * 4) + 2048, &a));
   double *Lbuf = a.take<double>(mat * P), *Sbuf = a.take<double>(mat * P), *Dbuf = a.take<double>(mat * P),
          *Lkeep = a.take<double>(mat * P);
   double *dx = a.take<double>(n), *dls = a.take<double>(P);
   int *info = a.take<int>(P);
-  double *stage = h->device_ptrs ? nullptr : a.take<double>((size_t)n * n);
+  double *stage = h->device_ptrs ? nullptr : a.take<double>((size_t)2 * P * n * n);
   if (!info || (!h->device_ptrs && !stage)) BAD_ARG(h, 1002, "chol_tangent: workspace exhausted");
   GPB_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int) * P, h->stream));
   RC(to_device(h, x1, dx, n));
@@ -290,12 +290,13 @@ int chol_tangent_common(Handle *h, int n, const double *x1, double alpha, const 
       RC(launch_unpack(h, n, n, Lkeep + q * mat, np, L + q * nn, n, 1, 0.0));
       RC(launch_unpack(h, n, n, Sbuf + q * mat, np, dLdl + q * nn, n, 1, 0.0));
     } else {
-      RC(launch_unpack(h, n, n, Lkeep + q * mat, np, stage, n, 1, 0.0));
-      RC(from_device(h, stage, L + q * nn, nn * sizeof(double)));
-      GPB_CUDA(h, cudaStreamSynchronize(h->stream));
-      RC(launch_unpack(h, n, n, Sbuf + q * mat, np, stage, n, 1, 0.0));
-      RC(from_device(h, stage, dLdl + q * nn, nn * sizeof(double)));
-      GPB_CUDA(h, cudaStreamSynchronize(h->stream));
+      // both matrices of a table are unpacked into one staging area and leave in back-to-back asynchronous copies;
+      // the only synchronisation is the one at the end (round 1 did unpack -> copy -> sync per matrix)
+      double *sl = stage + (size_t)q * 2 * nn, *sd = sl + nn;
+      RC(launch_unpack(h, n, n, Lkeep + q * mat, np, sl, n, 1, 0.0));
+      RC(launch_unpack(h, n, n, Sbuf + q * mat, np, sd, n, 1, 0.0));
+      RC(from_device(h, sl, L + q * nn, nn * sizeof(double)));
+      RC(from_device(h, sd, dLdl + q * nn, nn * sizeof(double)));
     }
   }
   GPB_CUDA(h, cudaStreamSynchronize(h->stream));  // info_out_host is valid from here
@@ -353,33 +354,34 @@ extern "C" int gpb200_approx_Lz(gpb200_handle_t h, int n, double l, int P, const
   // lp and the pointer tables are always host arrays; the tables they point to follow the pointer mode
   const int lidx = bracket(l, P, lp);
   const size_t nn = (size_t)n * n;
-  const int np = round_up(n, TILE);
   Arena a;
-  RC(ws_reserve(h, 6 * pad256(nn * 8) + 2 * pad256((size_t)np * np * 8) + 4 * pad256(np * 8), &a));
+  const int nchunk = hermite_matvec_chunks(n);
+  RC(ws_reserve(h, (h->device_ptrs ? 0 : 4) * pad256(nn * 8) + (z ? 0 : 1) * pad256(nn * 8) + pad256((size_t)nchunk * n * 16) +
+                       4 * pad256((size_t)n * 8) + 1024, &a));
   const double *t[4] = {Ls[lidx], Ls[lidx + 1], dLdls[lidx], dLdls[lidx + 1]};
   const double *d[4];
   for (int q = 0; q < 4; q++) {
     if (h->device_ptrs) d[q] = t[q];
     else {
       double *s = a.take<double>(nn);
+      if (!s) BAD_ARG(h, 1002, "approx_L: workspace exhausted");
       RC(to_device(h, t[q], s, nn));
       d[q] = s;
     }
   }
-  double *v = a.take<double>(nn), *dv = a.take<double>(nn);
-  RC(launch_hermite(h, (long long)nn, n, d[0], d[1], d[2], d[3], lp[lidx], lp[lidx + 1], l, v, z ? dv : nullptr));
   if (!z) {  // approx_L proper: return the interpolated factor in vz
+    double *v = a.take<double>(nn);
+    if (!v) BAD_ARG(h, 1002, "approx_L: workspace exhausted");
+    RC(launch_hermite(h, (long long)nn, n, d[0], d[1], d[2], d[3], lp[lidx], lp[lidx + 1], l, v, nullptr));
     RC(from_device(h, v, vz, nn * sizeof(double)));
     return finish(h);
   }
-  double *Vp = a.take<double>((size_t)np * np), *Dp = a.take<double>((size_t)np * np);
-  double *dz = a.take<double>(np), *o1 = a.take<double>(np), *o2 = a.take<double>(np);
-  RC(launch_pack(h, n, n, v, n, np, np, Vp, 2, 0.0));
-  RC(launch_pack(h, n, n, dv, n, np, np, Dp, 2, 0.0));
+  // approx_Lz: one fused pass over the four tables, the interpolated factor is never materialised
+  double *part = a.take<double>((size_t)nchunk * n * 2);
+  double *dz = a.take<double>(n), *o1 = a.take<double>(n), *o2 = a.take<double>(n);
+  if (!o2) BAD_ARG(h, 1002, "approx_Lz: workspace exhausted");
   RC(to_device(h, z, dz, n));
-  RC(launch_trmv_lower_n(h, np, Vp, 0, dz, 0, n, o1, 0, 1));
-  // the padded diagonal of Dp is 1 (identity padding) but z is zero there, so it contributes nothing
-  RC(launch_trmv_lower_n(h, np, Dp, 0, dz, 0, n, o2, 0, 1));
+  RC(launch_hermite_matvec(h, n, d[0], d[1], d[2], d[3], lp[lidx], lp[lidx + 1], l, dz, part, o1, dvdl_z ? o2 : nullptr));
   RC(from_device(h, o1, vz, n * sizeof(double)));
   if (dvdl_z) RC(from_device(h, o2, dvdl_z, n * sizeof(double)));
   return finish(h);

@@ -59,6 +59,9 @@ int launch_gemv_t(Handle *h, int rows, int cols, const double *V, long long ldv,
                   double *out);
 int launch_hermite(Handle *h, long long len, int n, const double *y1, const double *y2, const double *k1,
                    const double *k2, double x1, double x2, double l, double *v, double *dvdl);
+int hermite_matvec_chunks(int n);
+int launch_hermite_matvec(Handle *h, int n, const double *y1, const double *y2, const double *k1, const double *k2, double x1,
+                          double x2, double l, const double *z, double *part, double *vz, double *dvz);
 int launch_sumsq_logdiag(Handle *h, int n, const double *z, const double *L, long long ldl, double *out2);
 
 // small.cu

@@ -389,6 +389,52 @@ __global__ void hermite_kernel(long long len, int n, const double *__restrict__ 
   }
 }
 
+// approx_Lz fused (models/cubic_interpolated_gp.hpp:46-72): the four tables are read ONCE and the interpolated factor
+// is never stored -- each thread owns a row i, walks a chunk of the columns j <= i, forms v_ij and dv_ij/dl from
+// (y1, y2, k1, k2)_ij in registers and accumulates v_ij z_j and dv_ij z_j.  Consecutive threads read consecutive rows
+// (coalesced); blockIdx.y splits the columns so that a 4096 x 4096 table still fills the GPU; the chunk sums are
+// added in a fixed order by hermite_matvec_reduce_kernel.  HBM-bound: 4 * 8 * n^2 / 2 bytes.
+__global__ void __launch_bounds__(128) hermite_matvec_kernel(int n, const double *__restrict__ y1, const double *__restrict__ y2,
+                                                             const double *__restrict__ k1, const double *__restrict__ k2,
+                                                             double x1, double x2, double l, const double *__restrict__ z,
+                                                             double *__restrict__ part) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int nchunk = gridDim.y;
+  const int per = (n + nchunk - 1) / nchunk;
+  const int j0 = blockIdx.y * per, j1 = min(n, j0 + per);
+  const double dx = x2 - x1, t = (l - x1) / dx, dtdl = 1.0 / dx;
+  const double omt = 1.0 - t, tomt = t * omt;
+  double sv = 0.0, sd = 0.0;
+  if (i < n) {
+    const int jend = min(j1, i + 1);
+    for (int j = j0; j < jend; j++) {
+      const long long q = i + (long long)j * n;
+      const double a1 = y1[q], a2 = y2[q];
+      const double a = k1[q] * dx - (a2 - a1);
+      const double bb = -k2[q] * dx + (a2 - a1);
+      const double vv = omt * a1 + t * a2 + tomt * (a * omt + bb * t);
+      const double dd = (bb * (2 - 3 * t) * t + a * (1 + t * (-4 + 3 * t)) - a1 + a2) * dtdl;
+      const double zj = z[j];
+      sv = fma(vv, zj, sv);
+      sd = fma(dd, zj, sd);
+    }
+    part[((long long)blockIdx.y * n + i) * 2] = sv;
+    part[((long long)blockIdx.y * n + i) * 2 + 1] = sd;
+  }
+}
+__global__ void hermite_matvec_reduce_kernel(int n, int nchunk, const double *__restrict__ part, double *__restrict__ vz,
+                                             double *__restrict__ dvz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0, b = 0.0;
+  for (int c = 0; c < nchunk; c++) {
+    a += part[((long long)c * n + i) * 2];
+    b += part[((long long)c * n + i) * 2 + 1];
+  }
+  vz[i] = a;
+  if (dvz) dvz[i] = b;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 int launch_trmv_lower_n(Handle *h, int np, const double *W, long long stride, const double *y, long long y_stride,
                         int n_valid, double *z, long long z_stride, int batch) {
@@ -594,4 +640,20 @@ int launch_hermite(Handle *h, long long len, int n, const double *y1, const doub
   return 0;
 }
 
+}  // namespace gpb
+
+namespace gpb {
+int hermite_matvec_chunks(int n) { return std::max(1, std::min(64, (2 * 148 * 128 + n - 1) / std::max(n, 1))); }
+
+int launch_hermite_matvec(Handle *h, int n, const double *y1, const double *y2, const double *k1, const double *k2, double x1,
+                          double x2, double l, const double *z, double *part, double *vz, double *dvz) {
+  const int nchunk = hermite_matvec_chunks(n);
+  ProfScope ps__(h, PC_SOLVE);
+  dim3 grid((n + 127) / 128, nchunk);
+  hermite_matvec_kernel<<<grid, 128, 0, h->stream>>>(n, y1, y2, k1, k2, x1, x2, l, z, part);
+  GPB_LAUNCH_CHECK(h);
+  hermite_matvec_reduce_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, nchunk, part, vz, dvz);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
 }  // namespace gpb

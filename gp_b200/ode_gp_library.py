@@ -10,6 +10,7 @@ conditioned by the tiled Cholesky; nothing is computed on the host.
 from __future__ import annotations
 
 import numpy as np
+import scipy.linalg as sla
 
 from . import capi
 
@@ -83,14 +84,21 @@ def sample_derivs(params, ynoise, ti, rng=None, seed=None, handle=None):
     return mu + h.trmv_lower(L, rng.standard_normal(mu.shape[0]))
 
 
-def create_p_dotXnS(Xn_list, mn, Kn, theta, rng=None, handle=None):
+def create_p_dotXnS(Xn_list, mn, Kn, theta, rng=None, handle=None, incremental=True):
     """R/ode_gp_library.R:43-93: closure that, given a new state x*, returns the conditional normal
     of the derivative there given the data and every derivative already drawn, then draws from it.
 
-    Differences from the R text, all of them benign: the pre-factorisation of K_XX + 1e-6 I is a GPU
-    Cholesky instead of qr() (:55-57); `rnorm(1, mean, condVar)` passes a VARIANCE as sd (:84,
-    SURVEY Appendix A.3) -- reproduced by default (sd_is_variance=True on the returned closure).
-    Returns the closure; each call returns {"mu", "sigma", "dot_xs"} like the reference (:91).
+    Same values as the R text, less work per call (incremental=True, the default; row f-4 of SURVEY 8): the reference
+    rebuilds the whole i x i joint covariance of the star points, re-solves all i cross-covariance columns against
+    K_XX and inverts the (i-1) x (i-1) leading block inside condMVN on EVERY call (O(i N^2 + i^3)).  Here each call
+    solves only for the NEW column (one GPU potrs, N^2) and extends the lower Cholesky factor of the star points'
+    covariance by one row -- a bordered ("rank-1 growth") update, O(i^2) -- from which the conditional mean and
+    variance of the new point given all earlier draws drop out:  l = Lc^-1 k,  mean = m_i + l.w,  var = k_ii - l.l,
+    with w = Lc^-1 (dot_Xs - m) grown the same way.  incremental=False is the literal re-solve (kept for the test).
+
+    Other differences from the R text, all benign: the pre-factorisation of K_XX + 1e-6 I is a GPU Cholesky instead
+    of qr() (:55-57); `rnorm(1, mean, condVar)` passes a VARIANCE as sd (:84) -- reproduced by
+    default (sd_is_variance=True on the returned closure).  Each call returns {"mu", "sigma", "dot_xs"} (:91).
     """
     h = handle or capi.default_handle()
     rng = rng or np.random.default_rng()
@@ -103,11 +111,9 @@ def create_p_dotXnS(Xn_list, mn, Kn, theta, rng=None, handle=None):
     K_XX_1_mn = h.potrs(L, mn)
     K_XX_1_Kn = h.potrs(L, Kn)
     state = {"i": 1, "K_XsX": np.zeros((0, N)), "K_XsXs": np.zeros((0, 0)), "Xs": np.zeros((0, D)),
-             "dot_Xs": np.zeros(0)}
+             "dot_Xs": np.zeros(0), "S": np.zeros((N, 0)), "Lc": np.zeros((0, 0)), "w": np.zeros(0)}
 
-    def p_dotXnS(xs_vec, sd_is_variance=True):
-        xs = np.asarray(xs_vec, dtype=np.float64).reshape(1, D)
-        st = state
+    def step_literal(xs, st):
         st["K_XsX"] = np.vstack([st["K_XsX"], h.gram_ard(xs, X, float(theta[0]), theta[1])])
         kss = h.gram_ard(xs, xs, float(theta[0]), theta[1])
         if st["Xs"].shape[0]:
@@ -122,13 +128,56 @@ def create_p_dotXnS(Xn_list, mn, Kn, theta, rng=None, handle=None):
         K = (K + K.T) / 2 + 1e-6 * np.eye(K.shape[0])
         i = st["i"]
         if i == 1:
-            cmean, cvar = m[0], K[0, 0]
+            return m[0], K[0, 0]
+        # condMVN(m, K, i, 1:(i-1), c(dot_Xs)): last point given all earlier draws
+        cm, cv = h.cond_mvn(m, K, i - 1, st["dot_Xs"])
+        return cm[0], cv[0, 0]
+
+    def step_incremental(xs, st):
+        i = st["i"]
+        a = h.gram_ard(xs, X, float(theta[0]), theta[1])              # 1 x N
+        s = h.potrs(L, a.ravel().copy())                              # the NEW column of solve(K_XX, t(K_XsX))
+        A = np.vstack([st["K_XsX"], a])
+        S = np.column_stack([st["S"], s])
+        m_new = float(a.ravel() @ K_XX_1_mn)
+        kss = h.gram_ard(st["Xs"], xs, float(theta[0]), theta[1]).ravel() if st["Xs"].shape[0] else np.zeros(0)
+        kself = float(h.gram_ard(xs, xs, float(theta[0]), theta[1])[0, 0])
+        aK = a @ K_XX_1_Kn                                            # 1 x N
+        left = (a @ S - aK @ S).ravel()                               # row i of  K_XsX (I - K_XX^-1 Kn) K_XX^-1 K_XXs
+        right = (A @ s - A @ (K_XX_1_Kn @ s)).ravel()                 # column i of the same (not symmetric before averaging)
+        krow = np.concatenate([kss, [kself]]) - 0.5 * (left + right)
+        krow[i - 1] += 1e-6
+        if i == 1:
+            l_row = np.zeros(0)
+            cmean, cvar = m_new, krow[0]
         else:
-            # condMVN(m, K, i, 1:(i-1), c(dot_Xs)): last point given all earlier draws
-            cm, cv = h.cond_mvn(m, K, i - 1, st["dot_Xs"])
-            cmean, cvar = cm[0], cv[0, 0]
+            l_row = sla.solve_triangular(st["Lc"], krow[:i - 1], lower=True, check_finite=False)
+            cmean = m_new + float(l_row @ st["w"])
+            cvar = krow[i - 1] - float(l_row @ l_row)
+        if not cvar > 0.0:
+            # the bordered factor's new pivot: the joint covariance of the star points is not positive definite
+            # (condMVN's explicit inverse would go on and return a negative variance)
+            raise capi.NotPositiveDefiniteError("create_p_dotXnS", i)
+        st["K_XsX"], st["S"] = A, S
+        st["_pending"] = (l_row, cvar, cmean)
+        return cmean, cvar
+
+    def p_dotXnS(xs_vec, sd_is_variance=True):
+        xs = np.asarray(xs_vec, dtype=np.float64).reshape(1, D)
+        st = state
+        cmean, cvar = (step_incremental if incremental else step_literal)(xs, st)
         sd = cvar if sd_is_variance else np.sqrt(max(cvar, 0.0))
         dot_xs = cmean + sd * rng.standard_normal()
+        i = st["i"]
+        if incremental:
+            l_row, cv, cm = st.pop("_pending")
+            d = np.sqrt(max(cv, 0.0))
+            Lc = np.zeros((i, i))
+            Lc[:i - 1, :i - 1] = st["Lc"]
+            Lc[i - 1, :i - 1] = l_row
+            Lc[i - 1, i - 1] = d
+            st["Lc"] = Lc
+            st["w"] = np.append(st["w"], (dot_xs - cm) / d if d > 0 else 0.0)
         st["i"] = i + 1
         st["Xs"] = np.vstack([st["Xs"], xs])
         st["dot_Xs"] = np.append(st["dot_Xs"], dot_xs)

@@ -182,12 +182,17 @@ def test_create_p_dotXnS_sequential_sampler(handle):
         def __init__(self, v): self.v = list(v)
         def standard_normal(self): return self.v.pop(0)
 
+    # incremental=True grows the Cholesky factor of the star points' covariance by one row per call (f-4);
+    # incremental=False is the literal rebuild-and-re-solve of R/ode_gp_library.R:65-92: same numbers
     f = lib.create_p_dotXnS([Xn], mn, Kn, theta, rng=FixedRng(normals), handle=handle)
+    fl = lib.create_p_dotXnS([Xn], mn, Kn, theta, rng=FixedRng(normals), handle=handle, incremental=False)
     fr = o.create_p_dotXnS([Xn], mn, Kn, theta, normals)
     for xs in (0.3, 0.9, 1.7, 2.5, 0.5, 4.0):
-        a, b = f([xs]), fr([xs])
-        assert abs(a["mu"] - b["mu"]) <= 1e-6 * max(1.0, abs(b["mu"]))
-        assert abs(a["sigma"] - b["sigma"]) <= 1e-6 * max(1e-6, abs(b["sigma"]))
+        a, c, b = f([xs]), fl([xs]), fr([xs])
+        for got in (a, c):
+            assert abs(got["mu"] - b["mu"]) <= 1e-6 * max(1.0, abs(b["mu"]))
+            assert abs(got["sigma"] - b["sigma"]) <= 1e-6 * max(1e-6, abs(b["sigma"]))
+            assert abs(got["dot_xs"] - b["dot_xs"]) <= 1e-6 * max(1.0, abs(b["dot_xs"]))
     from gp_b200 import NotPositiveDefiniteError
     mn_q, Kn_q = o.p_dotXn_solve(tn, Xn, (1.2, 1.0), 0.1)       # quirk-affected, indefinite Kn
     fq = lib.create_p_dotXnS([Xn], mn_q, Kn_q, (1.2, [1.0]), rng=FixedRng(normals), handle=handle)
