@@ -9,6 +9,28 @@ using namespace gpb;
 // =================================================================================================
 extern "C" int gpb200_version(void) { return 100; }
 
+namespace {
+void free_handle(gpb200_handle_s *h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (h->gstream) { cudaStreamSynchronize(h->gstream); cudaStreamDestroy(h->gstream); }
+  if (h->pstream) { cudaStreamSynchronize(h->pstream); cudaStreamDestroy(h->pstream); }
+  if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
+  for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->mg_events) cudaEventDestroy(e);
+  if (h->g_in) cudaEventDestroy(h->g_in);
+  if (h->g_out) cudaEventDestroy(h->g_out);
+  if (h->stream_switch) cudaEventDestroy(h->stream_switch);
+  if (h->ws) cudaFree(h->ws);
+  if (h->latent_L) cudaFree(h->latent_L);
+  if (h->info_slot) cudaFree(h->info_slot);
+  for (auto &kv : h->task_cache) cudaFree(kv.second.first);
+  delete h;
+}
+}  // namespace
+
 extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (!out) return -1;
   *out = nullptr;
@@ -20,18 +42,21 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1000;
   if (prop.major < 10) return -1003;  // built for sm_100a only
-  if (cudaSetDevice(device) != cudaSuccess) return -1000;
+  DeviceGuard guard(device);
+  if (!guard.ok) return -1000;
   gpb200_handle_s *h = new (std::nothrow) gpb200_handle_s();
   if (!h) return -1002;
   h->device = device;
-  if (panel_smem_setup(h) || gemm_smem_setup(h) || small_smem_setup(h)) { delete h; return -1000; }
+  if (panel_smem_setup(h) || gemm_smem_setup(h) || small_smem_setup(h)) { free_handle(h); return -1000; }
   if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) { delete h; return -1000; }
+      cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->stream_switch, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc(&h->info_slot, sizeof(int)) != cudaSuccess) { free_handle(h); return -1000; }
   {
     int lo = 0, hi = 0;  // numerically lowest value = highest priority
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&h->pstream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return -1000; }
+        cudaStreamCreateWithPriority(&h->pstream, cudaStreamNonBlocking, hi) != cudaSuccess) { free_handle(h); return -1000; }
   }
   const char *cp = getenv("GPB200_CHOL_PANEL");  // same meaning as gpb200_set_chol_panel_tiles
   if (cp && cp[0] >= '0' && cp[0] <= '9') h->chol_panel_override = atoi(cp);
@@ -39,6 +64,8 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (sk && sk[0] == '0') h->small_kernel = 0;
   const char *la = getenv("GPB200_LOOKAHEAD");
   if (la && la[0] == '0') h->lookahead = 0;
+  const char *lb = getenv("GPB200_LOOKAHEAD_MAXB");
+  if (lb && lb[0] >= '0' && lb[0] <= '9') h->lookahead_max_batch = atoi(lb);
   const char *qw = getenv("GPB200_QUARTER_WAVES");
   if (qw && qw[0] >= '0' && qw[0] <= '9') h->quarter_below_waves = atoi(qw);
   const char *gc = getenv("GPB200_GEMM_CFG");  // tuning knob, same meaning as gpb200_set_gemm_config
@@ -46,7 +73,7 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   const char *tp = getenv("GPB200_TRSM_PIPELINED");
   if (tp && tp[0] == '0') h->trsm_pipelined = 0;
   const char *pv = getenv("GPB200_PANEL_V1");
-  if (pv && (pv[0] == '1' || pv[0] == '2')) h->panel_impl = pv[0] - '0';
+  if (pv && pv[0] == '1') h->panel_impl = 1;
   const char *tm = getenv("GPB200_TRSM_MT");
   if (tm && (tm[0] == '1' || tm[0] == '2')) h->trsm_mt_override = tm[0] - '0';
   const char *ng = getenv("GPB200_NO_GRAPH");
@@ -57,25 +84,22 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
 
 extern "C" int gpb200_destroy(gpb200_handle_t h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
-  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
-  if (h->gstream) { cudaStreamSynchronize(h->gstream); cudaStreamDestroy(h->gstream); }
-  if (h->pstream) { cudaStreamSynchronize(h->pstream); cudaStreamDestroy(h->pstream); }
-  for (cudaEvent_t e : h->sync_events) cudaEventDestroy(e);
-  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-  if (h->g_in) cudaEventDestroy(h->g_in);
-  if (h->g_out) cudaEventDestroy(h->g_out);
-  if (h->ws) cudaFree(h->ws);
-  if (h->latent_L) cudaFree(h->latent_L);
-  for (auto &kv : h->task_cache) cudaFree(kv.second.first);
-  delete h;
+  DeviceGuard guard(h->device);
+  if (h->nccl_comm) gpb200_mg_comm_destroy(h);
+  free_handle(h);
   return 0;
 }
 
+// Switching streams keeps stream order: whatever this handle enqueued on the old stream (it all works out of one
+// workspace) completes before anything it enqueues on the new one starts -- an event, no host synchronisation.
 extern "C" int gpb200_set_stream(gpb200_handle_t h, void *s) {
-  if (!h) return -1;
-  h->stream = reinterpret_cast<cudaStream_t>(s);
+  CHECK_H(h);
+  cudaStream_t ns = reinterpret_cast<cudaStream_t>(s);
+  if (ns != h->stream) {
+    GPB_CUDA(h, cudaEventRecord(h->stream_switch, h->stream));
+    GPB_CUDA(h, cudaStreamWaitEvent(ns, h->stream_switch, 0));
+    h->stream = ns;
+  }
   return 0;
 }
 extern "C" int gpb200_set_pointer_mode(gpb200_handle_t h, int dev) {
@@ -270,6 +294,7 @@ extern "C" int gpb200_potrf(gpb200_handle_t h, int n, double *A, int lda) {
   CHECK_H(h);
   if (n < 0) BAD_ARG(h, 2, "potrf: negative n");
   if (lda < std::max(1, n)) BAD_ARG(h, 4, "potrf: lda < n");
+  if (n > MAX_DENSE_N) BAD_ARG(h, 2, "potrf: n above 65407 is not supported by the dense entry points (use the block-cyclic path)");
   if (n == 0) return 0;
   const int np = round_up(n, TILE);
   Arena a;
@@ -393,6 +418,7 @@ extern "C" int gpb200_trsm_lower(gpb200_handle_t h, int n, int nrhs, const doubl
   if (n < 0 || nrhs < 0) BAD_ARG(h, 2, "trsm_lower: negative size");
   if (ldl < std::max(1, n) || ldb < std::max(1, n)) BAD_ARG(h, 5, "trsm_lower: bad leading dimension");
   if (n == 0 || nrhs == 0) return 0;
+  if (n > MAX_DENSE_N || nrhs > MAX_DENSE_N) BAD_ARG(h, 2, "trsm_lower: sizes above 65407 are not supported");
   return solve_common(h, n, nrhs, L, ldl, B, ldb, false);
 }
 
@@ -401,6 +427,7 @@ extern "C" int gpb200_potrs(gpb200_handle_t h, int n, int nrhs, const double *L,
   if (n < 0 || nrhs < 0) BAD_ARG(h, 2, "potrs: negative size");
   if (ldl < std::max(1, n) || ldb < std::max(1, n)) BAD_ARG(h, 5, "potrs: bad leading dimension");
   if (n == 0 || nrhs == 0) return 0;
+  if (n > MAX_DENSE_N || nrhs > MAX_DENSE_N) BAD_ARG(h, 2, "potrs: sizes above 65407 are not supported");
   return solve_common(h, n, nrhs, L, ldl, B, ldb, true);
 }
 

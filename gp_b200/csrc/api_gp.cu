@@ -203,13 +203,11 @@ extern "C" int gpb200_lml_grad(gpb200_handle_t h, int n, const double *x, const 
                                double jitter, double *lml, double *grad) {
   CHECK_H(h);
   if (h->device_ptrs) {
-    // info must live on the device in device-pointer mode; use a private slot
-    int *dinfo = nullptr;
-    GPB_CUDA(h, cudaMalloc(&dinfo, sizeof(int)));
-    int rc = gpb200_lml_grad_batched(h, n, 1, x, 0, y, 0, theta, jitter, grad != nullptr, lml, grad, dinfo);
+    // info must live on the device in device-pointer mode: the handle's persistent slot (no allocation, nothing
+    // that synchronises the device); only the read of the status word waits for the handle's stream
+    int rc = gpb200_lml_grad_batched(h, n, 1, x, 0, y, 0, theta, jitter, grad != nullptr, lml, grad, h->info_slot);
     int hinfo = 0;
-    if (rc == 0) rc = read_info(h, dinfo, &hinfo);
-    cudaFree(dinfo);
+    if (rc == 0) rc = read_info(h, h->info_slot, &hinfo);
     return rc ? rc : hinfo;
   }
   int info = 0;
@@ -322,6 +320,7 @@ extern "C" int gpb200_rbf_cov_chol_batched(gpb200_handle_t h, int n, const doubl
   if (n < 0) BAD_ARG(h, 2, "rbf_cov_chol_batched: negative n");
   if (P < 0) BAD_ARG(h, 4, "rbf_cov_chol_batched: negative P");
   if (n == 0 || P == 0) return 0;
+  if (P > 65535 || n > MAX_DENSE_N) BAD_ARG(h, 4, "rbf_cov_chol_batched: at most 65535 tables of n <= 65407");
   return chol_tangent_common(h, n, x1, 1.0, ls, P, 1e-10, 0, L, dLdl, info);
 }
 
@@ -461,6 +460,7 @@ extern "C" int gpb200_gp_condition(gpb200_handle_t h, int n, int m, const double
                                    double jitter, double *mu, double *cov, int ldcov) {
   CHECK_H(h);
   if (n < 1 || m < 1) BAD_ARG(h, 2, "gp_condition: sizes must be >= 1");
+  if (n > MAX_DENSE_N || m > MAX_DENSE_N) BAD_ARG(h, 2, "gp_condition: sizes above 65407 are not supported");
   if (ldk < n || ldks < m || ldkss < m || ldcov < m) BAD_ARG(h, 5, "gp_condition: bad leading dimension");
   Arena a;
   const size_t stage = h->device_ptrs ? 0 : pad256((size_t)n * n * 8) + pad256((size_t)m * n * 8) + 2 * pad256((size_t)m * m * 8) + pad256(n * 8) + pad256(m * 8);
@@ -494,6 +494,7 @@ extern "C" int gpb200_cond_mvn(gpb200_handle_t h, int ng, int nd, const double *
                                const double *x_given, double *cond_mean, double *cond_var, int ldv) {
   CHECK_H(h);
   if (ng < 1 || nd < 1) BAD_ARG(h, 2, "cond_mvn: sizes must be >= 1");
+  if (ng > MAX_DENSE_N || nd > MAX_DENSE_N) BAD_ARG(h, 2, "cond_mvn: sizes above 65407 are not supported");
   const int N = ng + nd;
   if (lds < N || ldv < nd) BAD_ARG(h, 6, "cond_mvn: bad leading dimension");
   Arena a;

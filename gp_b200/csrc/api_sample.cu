@@ -40,6 +40,7 @@ extern "C" int gpb200_mvrnorm(gpb200_handle_t h, int ndraws, int m, const double
   CHECK_H(h);
   if (ndraws < 0) BAD_ARG(h, 2, "mvrnorm: negative number of draws");
   if (m < 1) BAD_ARG(h, 3, "mvrnorm: dimension must be >= 1");
+  if (m > MAX_DENSE_N) BAD_ARG(h, 3, "mvrnorm: dimensions above 65407 are not supported");
   if (lds < m) BAD_ARG(h, 6, "mvrnorm: lds < m");
   if (ldo < std::max(1, ndraws)) BAD_ARG(h, 10, "mvrnorm: ldo < ndraws");
   if (ndraws == 0) return 0;

@@ -29,6 +29,7 @@ struct Arena {
 };
 
 inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+constexpr int MAX_DENSE_N = 65535 - TILE;  // pack / unpack put the column index in gridDim.y (<= 65535)
 
 int ws_reserve(Handle *h, size_t bytes, Arena *a);
 
@@ -72,12 +73,25 @@ int read_info(Handle *h, const int *info_dev, int *out);
 
 }  // namespace gpb
 
-#define CHECK_H(h)                   \
-  do {                               \
-    if (!(h)) return -1;             \
-    (h)->err[0] = 0;                 \
-    if (cudaSetDevice((h)->device) != cudaSuccess) return -1000; \
-  } while (0)
+// Every entry point runs on the handle's device and gives the caller its own current device back on every return
+// path (a process may hold torch tensors or other handles on another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+#define CHECK_H(h)                                   \
+  if (!(h)) return -1;                               \
+  (h)->err[0] = 0;                                   \
+  DeviceGuard device_guard__((h)->device);      \
+  if (!device_guard__.ok) return -1000
 #define BAD_ARG(h, k, msg)                                  \
   do {                                                      \
     snprintf((h)->err, sizeof((h)->err), "%s", msg);       \
