@@ -193,7 +193,9 @@ static int tasks_chol_lookahead(Handle *h, int nt, int pt, TaskList *la1, TaskLi
 }
 
 bool chol_uses_lookahead(const Handle *h, int nt, int batch) {
-  return h->lookahead && h->pstream && batch <= h->lookahead_max_batch && nt >= 3;
+  // few tiles in flight: the panel chain, not the DMMA work, bounds the factorisation (with more items the pure
+  // left-looking schedule already fills the GPU and its deep-K updates are the more efficient GEMMs)
+  return h->lookahead && h->pstream && batch <= h->lookahead_max_batch && (long long)batch * nt <= 256 && nt >= 3;
 }
 int chol_lookahead_panel(const Handle *h, int nt) {
   return h->chol_panel_override > 0 ? std::min(nt, h->chol_panel_override) : 1;

@@ -841,6 +841,9 @@ int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, l
     dim3 grid(ntiles * 2, batch);
     trsm_ll_kernel<2><<<grid, 128, TrsmLL<2>::SMEM_BYTES, h->stream>>>(L, L, ld, stride, diag_off, c_off);
   } else {
+    // (an eight-warp, whole-tile form of the left-looking kernel was measured for this regime too: 611 us against 503 for
+    // 128 x 31 tiles -- with the C tile in shared memory the DMMA operands cost two shared-memory loads each, where the
+    // register-tile kernels feed A from registers; the round-1 kernels stay for batches)
     const int tpc = total >= 148 * 16 ? 4 : (total >= 148 * 6 ? 2 : 1);
     if (tpc == 1 || h->trsm_pipelined == 0) {
       dim3 grid(ntiles, batch);
