@@ -300,6 +300,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     h.set_profiling(True)
+    h.lib.gpb200_set_flop_counting(h._h, 1)
     launches0 = h.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -313,6 +314,8 @@ def main():
     launches = h.launch_count() - launches0
     prof = h.get_profile()
     h.set_profiling(False)
+    executed_flops = float(h.lib.gpb200_executed_gemm_flops(h._h))
+    h.lib.gpb200_set_flop_counting(h._h, 0)
     clocks = sampler.result()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -419,6 +422,8 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "peak_source": peak_src + " -- of measured",
                 "launches_per_step": gemm_count // max(K, 1), "kernel_ms_per_step": gemm_ms / K,
+                "executed_over_algorithmic": executed_flops / (gemm_flops_step * K) if gemm_flops_step else None,
+                "executed_tflops": executed_flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else None,
                 "kernel_share_of_step": gemm_ms / ms if ms > 0 else None,
                 "whole_step_tflops": value / world * float(N) ** 3 * 1e-12,
                 "whole_step_frac": value / world * float(N) ** 3 * 1e-12 / peak,

@@ -38,6 +38,8 @@ SIGNATURES = {
     "gpb200_set_gemm_config": (C.c_int, [_h, C.c_int]),
     "gpb200_set_profiling": (C.c_int, [_h, C.c_int]),
     "gpb200_get_profile": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
+    "gpb200_set_flop_counting": (C.c_int, [_h, C.c_int]),
+    "gpb200_executed_gemm_flops": (C.c_double, [_h]),
     "gpb200_debug_bench_panel": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gpb200_debug_panel_trace": (C.c_int, [_h, C.c_void_p]),
     "gpb200_kernel_eval": (C.c_int, [_h, C.c_int, _ll, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),

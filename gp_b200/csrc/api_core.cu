@@ -557,3 +557,13 @@ extern "C" int gpb200_debug_panel_trace(gpb200_handle_t h, long long *out2048) {
   GPB_CUDA(h, cudaDeviceSynchronize());
   return panel_trace_fetch(out2048);
 }
+
+// Accounting of the flops the DMMA GEMM launches really execute (host-side, from the task lists: 2 * tile area * k per CTA
+// after the CTA-uniform skipping).  on != 0 resets the counter and starts counting; the getter returns the running total.
+extern "C" int gpb200_set_flop_counting(gpb200_handle_t h, int on) {
+  if (!h) return -1;
+  h->count_flops = on ? 1 : 0;
+  h->executed_gemm_flops = 0.0;
+  return 0;
+}
+extern "C" double gpb200_executed_gemm_flops(gpb200_handle_t h) { return h ? h->executed_gemm_flops : 0.0; }

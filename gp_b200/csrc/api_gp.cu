@@ -31,6 +31,11 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
   // milliseconds with tens of GB allocated, so it is only consulted when the workspace must grow.
   // n <= 128: one CTA per item does the whole evaluation in shared memory (small.cu); no O(n^2) workspace at all
   const bool small = !sp.deriv && lml_small_applies(h, n);
+  if (small && h->device_ptrs && info && lml && (grad || !want_grad)) {
+    // device-pointer mode: the kernel reads the caller's arrays and writes the caller's results in place --
+    // ONE launch per call, no staging copies, no memset (the kernel writes every info word)
+    return launch_lml_small(h, n, x, x_stride, y, y_stride, theta, jitter, want_grad, lml, grad, info, B);
+  }
   const int zks = trmv_split_chunks(np, B);  // k-chunks of the split z = W y (small batches only)
   const size_t per_item = small ? 0 : pad256(mat * 8) * 2 + 3 * pad256(np * 8) + pad256((size_t)nparts * pw * 8) + (zks > 1 ? pad256((size_t)zks * np * 8) : 0) + 64;
   const size_t fixed = pad256((size_t)B * (x_stride ? ng : 0) * 8 + ng * 8) + pad256((size_t)B * (y_stride ? n : 0) * 8 + n * 8) +

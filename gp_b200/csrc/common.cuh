@@ -73,6 +73,9 @@ struct Handle {
   size_t ws_bytes = 0;
   // cached device-side task lists keyed by (kind, nt)
   std::map<long long, std::pair<TileTask *, std::vector<int>>> task_cache;
+  std::map<long long, std::vector<TileTask>> task_host;  // host copies (executed-flop accounting, gpb200_set_flop_counting)
+  int count_flops = 0;
+  double executed_gemm_flops = 0.0;  // flops the DMMA GEMM launches actually executed (after CTA-level skipping)
   // CUDA graphs of the launch sequence of small (launch-latency-bound) LML evaluations, keyed by the
   // problem signature; replayed on a handle-owned stream (the caller's stream may be the legacy
   // default stream, which cannot be captured).  Invalidated when the workspace moves.

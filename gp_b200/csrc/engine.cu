@@ -51,6 +51,7 @@ int upload_tasks(Handle *h, long long key, const std::vector<TileTask> &tasks, c
       GPB_CUDA(h, cudaMemcpyAsync(dev, tasks.data(), tasks.size() * sizeof(TileTask), cudaMemcpyHostToDevice, h->stream));
     GPB_CUDA(h, cudaStreamSynchronize(h->stream));
     it = h->task_cache.emplace(key, std::make_pair(dev, offsets)).first;
+    h->task_host[key] = tasks;
   }
   out->dev = it->second.first;
   out->offsets = &it->second.second;

@@ -18,6 +18,8 @@
 //                               of multi_normal_cholesky -> cholesky_decompose -> cov_exp_quad), for the
 //                               SE kernel and for the joint derivative-observation kernels
 //   NN                          products of the forward-mode tangent and of mvrnorm
+#include <algorithm>
+
 #include "common.cuh"
 #include "fastexp.cuh"
 
@@ -478,9 +480,40 @@ int gemm_nsplit(const Handle *h, int ntasks, int batch) {
   return c == 3 ? CfgQuarter::NSPLIT : (c == 2 ? CfgHalf8::NSPLIT : 1);
 }
 
+// Flops a launch really executes: per CTA 2 * TM * TN * k, with k shortened by the CTA-uniform skipping of triangular
+// operand tiles and zero for the skipped quadrant of symmetric diagonal tiles -- the same rules as in the kernel.
+static double executed_flops(const Handle *h, const TileTask *dev_tasks, int ntasks, int batch, int cfg) {
+  const TileTask *host = nullptr;
+  for (const auto &kv : h->task_cache) {
+    const TileTask *base = kv.second.first;
+    const auto it = h->task_host.find(kv.first);
+    if (it == h->task_host.end()) continue;
+    if (dev_tasks >= base && dev_tasks < base + it->second.size()) { host = it->second.data() + (dev_tasks - base); break; }
+  }
+  if (!host) return 0.0;
+  const int sm = cfg == 3 ? 2 : 1, sn = cfg == 1 ? 1 : 2;   // CTAs per task along m and n
+  const int tm = TILE / sm, tn = TILE / sn;
+  double total = 0.0;
+  for (int q = 0; q < ntasks; q++) {
+    const TileTask &t = host[q];
+    for (int mh = 0; mh < sm; mh++)
+      for (int nh = 0; nh < sn; nh++) {
+        if (sm > 1 && (t.flags & TF_DIAG) && mh < nh) continue;
+        int k = t.k_len;
+        const bool first = (sn > 1 && (t.flags & TF_B_TRI_FIRST) && nh == 1) || (sm > 1 && (t.flags & TF_A_TRI_FIRST) && mh == 1);
+        const bool last = (sn > 1 && (t.flags & TF_B_TRI_LAST) && nh == 0) || (sm > 1 && (t.flags & TF_A_TRI_LAST) && mh == 0);
+        if (first) k -= TILE / 2;
+        if (last) k -= TILE / 2;
+        total += 2.0 * tm * tn * (double)std::max(k, 0);
+      }
+  }
+  return total * batch;
+}
+
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
   if (ntasks <= 0 || batch <= 0) return 0;
   const int c = gemm_pick_cfg(h, ntasks, batch);
+  if (h->count_flops) h->executed_gemm_flops += executed_flops(h, p.tasks, ntasks, batch, c);
   if (c == 1) return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
   if (c == 3) return launch_cfg<CfgQuarter>(h, layout, epi, p, ntasks, batch);
   return launch_cfg<CfgHalf8>(h, layout, epi, p, ntasks, batch);

@@ -319,7 +319,7 @@ lml_small_kernel(int n, int n8, const double *__restrict__ x, long long x_stride
       grad[b * 3 + 1] = 0.5 * a2 * r[4] / (rho * rho * rho);
       grad[b * 3 + 2] = sigma * (r[2] - r[5]);
     }
-    if (s_info != 0 && s_info <= n && info[b] == 0) info[b] = s_info;
+    info[b] = (s_info != 0 && s_info <= n) ? s_info : 0;   // always written: the caller needs no memset
   }
 }
 

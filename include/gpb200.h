@@ -67,6 +67,12 @@ GPB200_API int gpb200_set_gemm_config(gpb200_handle_t h, int cfg);
 GPB200_API int gpb200_set_profiling(gpb200_handle_t h, int on);
 GPB200_API int gpb200_get_profile(gpb200_handle_t h, double *ms_out6, long long *count_out6);
 
+/* flops the DMMA tile-GEMM launches really executed since counting was switched on (host-side accounting from the task
+ * lists: 2 x CTA tile area x contraction length per CTA, after the skipping of triangular / symmetric tile parts);
+ * bench.py reports it against the algorithmic count */
+GPB200_API int gpb200_set_flop_counting(gpb200_handle_t h, int on);
+GPB200_API double gpb200_executed_gemm_flops(gpb200_handle_t h);
+
 /* tuning aid (not a reference interface): times one panel kernel in isolation on `batch` synthetic
  * matrices of nt x nt 128-tiles.  what: 0 POTRF of a diagonal tile, 1 TRSM of the nt-1 tiles below it,
  * 2 inverse of the nt diagonal tiles.  ms_out[0] = mean device time per launch (CUDA events). */

@@ -174,3 +174,32 @@ def test_headline_n4096_scale_and_homogeneity_properties(handle):
     quad = -(l3[0] - l1[0]) / 1.5
     lhs = th[0, 0] * g1[0, 0] + th[0, 2] * g1[0, 2]
     assert abs(lhs - (quad - n)) <= 1e-9 * max(abs(quad), n)
+
+
+def test_c3_and_c4_at_their_stated_scale(handle):
+    """BASELINE configs 3 and 4 at FULL size on one GPU (the multi-GPU runs shard exactly these batches): C3 = 4 096
+    hyper-parameter draws of N = 2 048 on one (x, y); C4 = 256 independent groups of N = 1 024.  Sixteen items spread
+    over each batch (first, last, chunk boundaries of a 256-item split) are checked against the oracle; every item must
+    be positive definite and finite, and the batch result must not depend on how it is chunked."""
+    n, B = 2048, 4096
+    x, y = o.synth_xy(n, 3)
+    th = o.synth_theta(B, 3)
+    lml, grad, info = handle.lml_grad_batched(x, y, th)
+    assert np.all(info == 0) and np.all(np.isfinite(lml)) and np.all(np.isfinite(grad))
+    for b in (0, 1, 255, 256, 511, 512, 1023, 1024, 2047, 2048, 3071, 3072, 3583, 3584, 4094, 4095):
+        rv, rg = o.lml_grad_lapack(x, y, *th[b])
+        assert abs(lml[b] - rv) <= 1e-9 * abs(rv), (b, lml[b], rv)
+        assert relerr(grad[b], rg) < 1e-9, (b, grad[b], rg)
+    # the same draws evaluated as the 8-GPU run would shard them (512 per rank): identical values
+    lo, hi = 1536, 2048
+    l2, g2, _ = handle.lml_grad_batched(x, y, th[lo:hi])
+    assert np.array_equal(l2, lml[lo:hi]) and np.array_equal(g2, grad[lo:hi])
+    G, n4 = 256, 1024
+    xs, ys = zip(*[o.synth_xy(n4, 4 + g) for g in range(G)])
+    X = np.stack(xs); Y = np.stack(ys)
+    thg = o.synth_theta(G, 4)
+    lml4, grad4, info4 = handle.lml_grad_batched(X, Y, thg)
+    assert np.all(info4 == 0)
+    for g in (0, 1, 31, 32, 63, 64, 127, 128, 129, 191, 192, 223, 224, 254, 255, 100):
+        rv, rg = o.lml_grad_lapack(X[g], Y[g], *thg[g])
+        assert abs(lml4[g] - rv) <= 1e-9 * abs(rv) and relerr(grad4[g], rg) < 1e-9, g
