@@ -27,6 +27,7 @@ void free_handle(gpb200_handle_s *h) {
   if (h->latent_L) cudaFree(h->latent_L);
   if (h->info_slot) cudaFree(h->info_slot);
   for (auto &kv : h->task_cache) cudaFree(kv.second.first);
+  for (auto &kv : h->split_cache) if (kv.second.reg) cudaFree(kv.second.reg);
   delete h;
 }
 }  // namespace
@@ -74,6 +75,8 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (tp && tp[0] == '0') h->trsm_pipelined = 0;
   const char *pv = getenv("GPB200_PANEL_V1");
   if (pv && pv[0] == '1') h->panel_impl = 1;
+  const char *ds = getenv("GPB200_DIAG_SPLIT");
+  if (ds && ds[0] == '0') h->diag_split = 0;
   const char *tm = getenv("GPB200_TRSM_MT");
   if (tm && (tm[0] == '1' || tm[0] == '2')) h->trsm_mt_override = tm[0] - '0';
   const char *ng = getenv("GPB200_NO_GRAPH");

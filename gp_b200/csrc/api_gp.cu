@@ -105,11 +105,13 @@ int lml_core(gpb200_handle_t h, const LmlSpec &sp, int B, const double *x, long 
         if (bc >= 32) RC(launch_trsv_blocked(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, np, bc));
         else RC(launch_trsv_sweep(h, np, Lbuf, Sbuf, mat, cy, ys, nullptr, n, zbuf, abuf, np, bc));
       }
+      int n1 = 0, n2 = 0;
+      RC(gemm_partial_layout(h, tl.at(0), ntasks, bc, &n1, &n2));
       if (sp.deriv)
-        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, ntasks, bc), cth, dlml + b0,
+        RC(launch_finalize_deriv(h, ng, sp.nblocks, np, want_grad, dvec, zbuf, abuf, partial, n1, n2, cth, dlml + b0,
                                  dgrad + (long long)b0 * ts, bc));
       else
-        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, ntasks * gemm_nsplit(h, ntasks, bc), cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
+        RC(launch_finalize(h, n, np, want_grad, dvec, zbuf, abuf, partial, n1, n2, cth, dlml + b0, dgrad + (long long)b0 * 3, bc));
     }
     return 0;
   };

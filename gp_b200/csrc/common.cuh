@@ -33,6 +33,12 @@ enum { TF_DIAG = 1,
        TF_B_TRI_LAST = 16,   // last  k-tile of B is zero where k_local > n_local
        TF_FULL_WEIGHT = 32 };// trace epilogue: the tile is NOT half of a symmetric pair (weight 1; reverse-mode adjoint)
 
+// a task list cut in two for the diagonal-split launch: symmetric diagonal tiles (TF_DIAG) and everything else
+struct SplitLists {
+  TileTask *reg = nullptr, *diag = nullptr;
+  int nreg = 0, ndiag = 0;
+};
+
 struct MatRef {
   double *p;
   long long ld;
@@ -74,6 +80,8 @@ struct Handle {
   // cached device-side task lists keyed by (kind, nt)
   std::map<long long, std::pair<TileTask *, std::vector<int>>> task_cache;
   std::map<long long, std::vector<TileTask>> task_host;  // host copies (executed-flop accounting, gpb200_set_flop_counting)
+  std::map<std::pair<const TileTask *, int>, SplitLists> split_cache;
+  int diag_split = 1;           // large batches: symmetric diagonal tiles run as 64x64 quarter CTAs in their own launch (env GPB200_DIAG_SPLIT)
   int count_flops = 0;
   double executed_gemm_flops = 0.0;  // flops the DMMA GEMM launches actually executed (after CTA-level skipping)
   // CUDA graphs of the launch sequence of small (launch-latency-bound) LML evaluations, keyed by the
@@ -181,6 +189,9 @@ enum GemmEpi { EPI_AXPBY = 0, EPI_TRACE = 1, EPI_TRACE_DERIV = 2 };
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch);
 int gemm_smem_setup(Handle *h);
 int gemm_nsplit(const Handle *h, int ntasks, int batch);
+// trace-epilogue partial records per item: n1 in the first region (item stride n1), n2 in a second region that starts
+// after all items' first-region records (the diagonal-split launch); n2 = 0 when the launch is not split
+int gemm_partial_layout(Handle *h, const TileTask *tasks, int ntasks, int batch, int *n1, int *n2);
 
 // panel kernels (panel.cu)
 int launch_potrf_tile(Handle *h, double *L, long long ld, long long stride, int tile_idx, int n,

@@ -19,6 +19,7 @@
 //                               SE kernel and for the joint derivative-observation kernels
 //   NN                          products of the forward-mode tangent and of mvrnorm
 #include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 #include "fastexp.cuh"
@@ -482,7 +483,7 @@ int gemm_nsplit(const Handle *h, int ntasks, int batch) {
 
 // Flops a launch really executes: per CTA 2 * TM * TN * k, with k shortened by the CTA-uniform skipping of triangular
 // operand tiles and zero for the skipped quadrant of symmetric diagonal tiles -- the same rules as in the kernel.
-static double executed_flops(const Handle *h, const TileTask *dev_tasks, int ntasks, int batch, int cfg) {
+static double executed_flops_host(const Handle *h, const TileTask *dev_tasks, int ntasks, int batch, int cfg_regular, int cfg_diag) {
   const TileTask *host = nullptr;
   for (const auto &kv : h->task_cache) {
     const TileTask *base = kv.second.first;
@@ -491,11 +492,12 @@ static double executed_flops(const Handle *h, const TileTask *dev_tasks, int nta
     if (dev_tasks >= base && dev_tasks < base + it->second.size()) { host = it->second.data() + (dev_tasks - base); break; }
   }
   if (!host) return 0.0;
-  const int sm = cfg == 3 ? 2 : 1, sn = cfg == 1 ? 1 : 2;   // CTAs per task along m and n
-  const int tm = TILE / sm, tn = TILE / sn;
   double total = 0.0;
   for (int q = 0; q < ntasks; q++) {
     const TileTask &t = host[q];
+    const int cfg = (t.flags & TF_DIAG) ? cfg_diag : cfg_regular;
+    const int sm = cfg == 3 ? 2 : 1, sn = cfg == 1 ? 1 : 2;   // CTAs per task along m and n
+    const int tm = TILE / sm, tn = TILE / sn;
     for (int mh = 0; mh < sm; mh++)
       for (int nh = 0; nh < sn; nh++) {
         if (sm > 1 && (t.flags & TF_DIAG) && mh < nh) continue;
@@ -510,10 +512,85 @@ static double executed_flops(const Handle *h, const TileTask *dev_tasks, int nta
   return total * batch;
 }
 
+// Diagonal split (large batches): the symmetric diagonal tiles of a launch -- one per block column of the Cholesky
+// update, nt of nt (nt + 1) / 2 in LAUUM -- go to a second launch of 64x64 quarter CTAs, which drop the redundant
+// upper-right quadrant and skip the zero half of BOTH triangular operand tiles; everything else stays on the 128x64
+// half-tile CTAs (2 % more efficient per executed flop, profiles/bench_r02*.json).  Same stream, back to back.
+static bool diag_split_applies(const Handle *h, int ntasks, int batch, int cfg) {
+  return h->diag_split && cfg == 2 && batch >= 16 && (long long)ntasks * batch >= 2048;
+}
+
+static int get_split(Handle *h, const TileTask *tasks, int ntasks, SplitLists *out) {
+  const auto key = std::make_pair(tasks, ntasks);
+  auto it = h->split_cache.find(key);
+  if (it == h->split_cache.end()) {
+    const TileTask *host = nullptr;
+    for (const auto &kv : h->task_cache) {
+      const TileTask *base = kv.second.first;
+      const auto ht = h->task_host.find(kv.first);
+      if (ht == h->task_host.end()) continue;
+      if (tasks >= base && tasks < base + ht->second.size()) { host = ht->second.data() + (tasks - base); break; }
+    }
+    SplitLists sl;
+    if (host) {
+      std::vector<TileTask> reg, diag;
+      for (int q = 0; q < ntasks; q++) ((host[q].flags & TF_DIAG) ? diag : reg).push_back(host[q]);
+      if (!reg.empty() && !diag.empty()) {
+        TileTask *dev = nullptr;
+        GPB_CUDA(h, cudaMalloc(&dev, (reg.size() + diag.size()) * sizeof(TileTask)));
+        GPB_CUDA(h, cudaMemcpy(dev, reg.data(), reg.size() * sizeof(TileTask), cudaMemcpyHostToDevice));
+        GPB_CUDA(h, cudaMemcpy(dev + reg.size(), diag.data(), diag.size() * sizeof(TileTask), cudaMemcpyHostToDevice));
+        sl.reg = dev;
+        sl.diag = dev + reg.size();
+        sl.nreg = (int)reg.size();
+        sl.ndiag = (int)diag.size();
+      }
+    }
+    it = h->split_cache.emplace(key, sl).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+int gemm_partial_layout(Handle *h, const TileTask *tasks, int ntasks, int batch, int *n1, int *n2) {
+  const int c = gemm_pick_cfg(h, ntasks, batch);
+  *n1 = ntasks * (c == 3 ? CfgQuarter::NSPLIT : (c == 2 ? CfgHalf8::NSPLIT : 1));
+  *n2 = 0;
+  if (diag_split_applies(h, ntasks, batch, c)) {
+    SplitLists sl;
+    int rc = get_split(h, tasks, ntasks, &sl);
+    if (rc) return rc;
+    if (sl.ndiag > 0) {
+      *n1 = sl.nreg * CfgHalf8::NSPLIT;
+      *n2 = sl.ndiag * CfgQuarter::NSPLIT;
+    }
+  }
+  return 0;
+}
+
 int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, int ntasks, int batch) {
   if (ntasks <= 0 || batch <= 0) return 0;
   const int c = gemm_pick_cfg(h, ntasks, batch);
-  if (h->count_flops) h->executed_gemm_flops += executed_flops(h, p.tasks, ntasks, batch, c);
+  if (diag_split_applies(h, ntasks, batch, c)) {
+    SplitLists sl;
+    int rc = get_split(h, p.tasks, ntasks, &sl);
+    if (rc) return rc;
+    if (sl.ndiag > 0) {
+      GemmParams pr = p, pd = p;
+      pr.tasks = sl.reg;
+      pr.ntasks = sl.nreg;
+      pd.tasks = sl.diag;
+      pd.ntasks = sl.ndiag;
+      if (epi != EPI_AXPBY && p.partial) pd.partial = p.partial + (long long)batch * sl.nreg * CfgHalf8::NSPLIT * (epi == EPI_TRACE_DERIV ? 8 : 4);
+      if (h->count_flops) {
+        h->executed_gemm_flops += executed_flops_host(h, p.tasks, ntasks, batch, 2, 3);
+      }
+      rc = launch_cfg<CfgHalf8>(h, layout, epi, pr, sl.nreg, batch);
+      if (rc) return rc;
+      return launch_cfg<CfgQuarter>(h, layout, epi, pd, sl.ndiag, batch);
+    }
+  }
+  if (h->count_flops) h->executed_gemm_flops += executed_flops_host(h, p.tasks, ntasks, batch, c, c);
   if (c == 1) return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
   if (c == 3) return launch_cfg<CfgQuarter>(h, layout, epi, p, ntasks, batch);
   return launch_cfg<CfgHalf8>(h, layout, epi, p, ntasks, batch);

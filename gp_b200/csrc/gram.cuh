@@ -46,9 +46,9 @@ int launch_trsv_sweep(Handle *h, int np, const double *L, const double *Wdiag, l
                       long long y_stride, const double *mu, int n_valid, double *z, double *acc, long long z_stride,
                       int batch);
 int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec, const double *z, const double *a,
-                    const double *partial, int ntasks, const double *theta, double *lml, double *grad, int batch);
+                    const double *partial, int ntasks, int ntasks2, const double *theta, double *lml, double *grad, int batch);
 int launch_finalize_deriv(Handle *h, int n_grid, int nblocks, int np, int want_grad, const double *dvec, const double *z,
-                          const double *a, const double *partial, int ntasks, const double *theta, double *lml,
+                          const double *a, const double *partial, int ntasks, int ntasks2, const double *theta, double *lml,
                           double *grad, int batch);
 int launch_pack(Handle *h, int rows, int cols, const double *src, long long lds, int rp, int cp, double *dst,
                 int mode, double diag_add);

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) trsv_update_kernel(long long ld, long lon
 // Deterministic finalisation, one CTA per batch item.
 __global__ void __launch_bounds__(256) finalize_kernel(int n, int np, int want_grad, const double *__restrict__ dvec,
                                                       const double *__restrict__ z, const double *__restrict__ a,
-                                                      const double *__restrict__ partial, int ntasks,
+                                                      const double *__restrict__ partial, int ntasks, int ntasks2,
                                                       const double *__restrict__ theta, double *__restrict__ lml,
                                                       double *__restrict__ grad) {
   __shared__ double red[8][6];
@@ -259,13 +259,21 @@ __global__ void __launch_bounds__(256) finalize_kernel(int n, int np, int want_g
       aa = fma(ai, ai, aa);
     }
   }
-  if (want_grad)
+  if (want_grad) {
     for (int q = tid; q < ntasks; q += 256) {
       const double *pp = partial + (b * ntasks + q) * 4;
       p0 += pp[0];
       p1 += pp[1];
       p2 += pp[2];
     }
+    const double *part2 = partial + (long long)gridDim.x * ntasks * 4;   // second region (diagonal-split launch)
+    for (int q = tid; q < ntasks2; q += 256) {
+      const double *pp = part2 + (b * ntasks2 + q) * 4;
+      p0 += pp[0];
+      p1 += pp[1];
+      p2 += pp[2];
+    }
+  }
   ld = warp_sum(ld); qf = warp_sum(qf); aa = warp_sum(aa);
   p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
   if (lane == 0) {
@@ -522,9 +530,9 @@ int launch_trsv_sweep(Handle *h, int np, const double *L, const double *Wdiag, l
 }
 
 int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec, const double *z, const double *a,
-                    const double *partial, int ntasks, const double *theta, double *lml, double *grad, int batch) {
+                    const double *partial, int ntasks, int ntasks2, const double *theta, double *lml, double *grad, int batch) {
   ProfScope ps__(h, PC_OTHER);
-  finalize_kernel<<<batch, 256, 0, h->stream>>>(n, np, want_grad, dvec, z, a, partial, ntasks, theta, lml, grad);
+  finalize_kernel<<<batch, 256, 0, h->stream>>>(n, np, want_grad, dvec, z, a, partial, ntasks, ntasks2, theta, lml, grad);
   GPB_LAUNCH_CHECK(h);
   return 0;
 }
@@ -535,7 +543,7 @@ int launch_finalize(Handle *h, int n, int np, int want_grad, const double *dvec,
 __global__ void __launch_bounds__(256) finalize_deriv_kernel(int n_grid, int nblocks, int np, int want_grad,
                                                             const double *__restrict__ dvec, const double *__restrict__ z,
                                                             const double *__restrict__ a,
-                                                            const double *__restrict__ partial, int ntasks,
+                                                            const double *__restrict__ partial, int ntasks, int ntasks2,
                                                             const double *__restrict__ theta, double *__restrict__ lml,
                                                             double *__restrict__ grad) {
   __shared__ double red[8][10];
@@ -553,12 +561,19 @@ __global__ void __launch_bounds__(256) finalize_deriv_kernel(int n_grid, int nbl
       if (blk == 0) v[2] = fma(ai, ai, v[2]); else if (blk == 1) v[3] = fma(ai, ai, v[3]); else v[4] = fma(ai, ai, v[4]);
     }
   }
-  if (want_grad)
+  if (want_grad) {
     for (int q = tid; q < ntasks; q += 256) {
       const double *pp = partial + (b * ntasks + q) * 8;
 #pragma unroll
       for (int c = 0; c < 5; c++) v[5 + c] += pp[c];
     }
+    const double *part2 = partial + (long long)gridDim.x * ntasks * 8;
+    for (int q = tid; q < ntasks2; q += 256) {
+      const double *pp = part2 + (b * ntasks2 + q) * 8;
+#pragma unroll
+      for (int c = 0; c < 5; c++) v[5 + c] += pp[c];
+    }
+  }
 #pragma unroll
   for (int c = 0; c < 10; c++) v[c] = warp_sum(v[c]);
   if (lane == 0)
@@ -580,10 +595,10 @@ __global__ void __launch_bounds__(256) finalize_deriv_kernel(int n_grid, int nbl
 }
 
 int launch_finalize_deriv(Handle *h, int n_grid, int nblocks, int np, int want_grad, const double *dvec, const double *z,
-                          const double *a, const double *partial, int ntasks, const double *theta, double *lml,
+                          const double *a, const double *partial, int ntasks, int ntasks2, const double *theta, double *lml,
                           double *grad, int batch) {
   ProfScope ps__(h, PC_OTHER);
-  finalize_deriv_kernel<<<batch, 256, 0, h->stream>>>(n_grid, nblocks, np, want_grad, dvec, z, a, partial, ntasks, theta,
+  finalize_deriv_kernel<<<batch, 256, 0, h->stream>>>(n_grid, nblocks, np, want_grad, dvec, z, a, partial, ntasks, ntasks2, theta,
                                                      lml, grad);
   GPB_LAUNCH_CHECK(h);
   return 0;

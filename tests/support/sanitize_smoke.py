@@ -32,5 +32,21 @@ h.gram_se(t, 1.0, 1.0, 0.1)
 h.gp_condition(h.gram_outer("QQ", t, t, 1.0), h.gram_outer("RQ", t, t, 1.0), h.gram_outer("RR", t, t, 1.0), np.sin(t), 0.01, 1e-8)
 tabs = [o.rbf_cov_chol(np.arange(40) * 0.9, l) for l in (0.5, 0.8)]
 h.approx_Lz(0.6, [0.5, 0.8], [a[0] for a in tabs], [a[1] for a in tabs], np.ones(40))
+# round 2: the one-CTA kernel (n <= 128), the single-matrix latency schedule (look-ahead streams, quarter tiles, left-looking
+# panel kernels, split mat-vec), a batch large enough for the diagonal-split launch, the reverse-mode adjoint
+xs, ys = o.synth_xy(100, 5)
+l2, g2, i2 = h.lml_grad_batched(xs, ys, o.synth_theta(4, 9))
+r2 = o.lml_grad(xs, ys, *o.synth_theta(4, 9)[3])
+assert abs(l2[3] - r2[0]) < 1e-9 * abs(r2[0])
+h.lml_grad_batched(xs[:37], ys[:37], o.synth_theta(2, 9), want_grad=False)
+x5, y5 = o.synth_xy(520, 6)
+l5, g5, _ = h.lml_grad_batched(x5, y5, o.synth_theta(1, 11))
+r5 = o.lml_grad(x5, y5, *o.synth_theta(1, 11)[0])
+assert abs(l5[0] - r5[0]) < 1e-9 * abs(r5[0]) and np.max(np.abs(g5[0] - r5[1])) < 1e-9 * np.max(np.abs(r5[1]))
+x3, y3 = o.synth_xy(300, 8)
+h.lml_grad_batched(x3, y3, o.synth_theta(24, 12))
+z = np.sin(np.arange(200) * 0.37)
+f = h.latent_forward(x, 1.1, 0.9, 1e-6, z)
+h.latent_backward(x, 1.1, 0.9, 1e-6, z, (y - f) / 0.09)
 print("sanitize smoke ok, launches", h.launch_count())
 h.close()
