@@ -25,6 +25,8 @@ from __future__ import annotations
 import ctypes as C
 import math
 
+import os
+
 import numpy as np
 
 TILE = 128
@@ -73,12 +75,15 @@ class GpuPanelBackend:
         self._chk(self.lib.gpb200_mg_panel_factor_col(self.h._h, n, col0, ncols, P.data_ptr(), ldp, jl, info.data_ptr()),
                   "mg_panel_factor_col")
 
-    def use_stream(self, stream):
-        self.h.set_stream(stream.cuda_stream)
+    def use_stream(self, stream, ordered=False):
+        """The block-cyclic schedule orders its streams with events of its own; an ordering edge on every switch would
+        serialise the panel chain with the trailing updates."""
+        self.h.set_stream(stream.cuda_stream, ordered=ordered)
 
-    def panel_update(self, n, pcol0, pncols, P, ldp, ccol0, cncols, Cp, ldc):
-        self._chk(self.lib.gpb200_mg_panel_update(self.h._h, n, pcol0, pncols, P.data_ptr(), ldp, ccol0, cncols,
-                                                  Cp.data_ptr(), ldc), "mg_panel_update")
+    def panel_update(self, n, pcol0, pncols, P, ldp, ccol0, cncols, Cp, ldc, jl0=0, jl1=None):
+        jl1 = cncols // TILE if jl1 is None else jl1
+        self._chk(self.lib.gpb200_mg_panel_update_cols(self.h._h, n, pcol0, pncols, P.data_ptr(), ldp, ccol0, cncols,
+                                                       Cp.data_ptr(), ldc, jl0, jl1), "mg_panel_update")
 
     def panel_trsv(self, n, col0, ncols, P, ldp, y, acc, z, scratch):
         self._chk(self.lib.gpb200_mg_panel_trsv(self.h._h, n, col0, ncols, P.data_ptr(), ldp, y.data_ptr(),
@@ -160,7 +165,7 @@ class GpuPanelBackend:
 class BlockCyclicGP:
     """Distributed factorisation and LML of one exact GP with a squared-exponential kernel."""
 
-    def __init__(self, n, panel_cols=512, backend=None, group=None, keep_all=False):
+    def __init__(self, n, panel_cols=512, backend=None, group=None, keep_all=False, split_update=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -178,6 +183,11 @@ class BlockCyclicGP:
         # keep_all: every rank keeps every broadcast panel (the gradient needs the whole factor on every rank; the
         # panels arrive anyway).  Otherwise two receive buffers are recycled.
         self.keep_all = bool(keep_all)
+        # split_update (native schedule): the owner of the next panel applies the arriving panel to its first tile column on
+        # the panel chain and to the others on a side stream
+        if split_update is None:
+            split_update = os.environ.get("GPB200_MG_SPLIT_UPDATE", "1") != "0"
+        self.split_update = bool(split_update)
         self.received = {}
         self.native = bool(getattr(backend, "native_comm", False))
         self.x_dev = None
@@ -295,8 +305,10 @@ class BlockCyclicGP:
         torch = be.torch
         main = torch.cuda.current_stream(be.device)
         if getattr(self, "_pstream", None) is None:
-            self._pstream = torch.cuda.Stream(device=be.device, priority=-1)
-        ps = self._pstream
+            self._pstream = torch.cuda.Stream(device=be.device, priority=-2)
+            self._ustream = torch.cuda.Stream(device=be.device, priority=-1)
+        ps, us = self._pstream, self._ustream
+        split = self.split_update
         be.use_stream(main)
         for p in self.my_panels():
             P = be.empty(self.ld(p), self.ncols(p))
@@ -329,18 +341,36 @@ class BlockCyclicGP:
             chunk = self.ld(p) * TILE
             flat = buf.reshape(-1)
             tickets = []
+            col_ready = {}
             be.use_stream(ps)
             if own == self.rank:
                 ps.wait_event(last_upd.get(p, built))
                 if prev_buf is not None:
                     for t in prev_tickets:
                         be.wait(t)
-                    be.panel_update(n, self.col0(p - 1), self.ncols(p - 1), prev_buf, self.ld(p - 1), self.col0(p), self.ncols(p),
-                                    buf, self.ld(p))
+                    upd = (n, self.col0(p - 1), self.ncols(p - 1), prev_buf, self.ld(p - 1), self.col0(p), self.ncols(p), buf,
+                           self.ld(p))
+                    if split and ntc > 1:
+                        # only tile column 0 has to be updated before the chain can go on; the other tile columns are
+                        # updated beside it (the POTRF / TRSM kernels of the chain leave most SMs idle)
+                        ready = torch.cuda.Event()
+                        ready.record(ps)
+                        us.wait_event(ready)
+                        be.use_stream(us)
+                        for jl in range(1, ntc):
+                            be.panel_update(*upd, jl0=jl, jl1=jl + 1)
+                            col_ready[jl] = torch.cuda.Event()
+                            col_ready[jl].record(us)
+                        be.use_stream(ps)
+                        be.panel_update(*upd, jl0=0, jl1=1)
+                    else:
+                        be.panel_update(*upd)
             elif not self.keep_all:
                 # a recycled receive buffer may still be read by trailing updates of panel p-2 on the main stream
                 ev = torch.cuda.Event(); ev.record(main); ps.wait_event(ev)
             for jl in range(ntc):
+                if jl in col_ready:
+                    ps.wait_event(col_ready[jl])
                 if own == self.rank:
                     be.panel_factor_col(n, self.col0(p), self.ncols(p), buf, self.ld(p), jl, self.info)
                 tickets.append(be.bcast(flat[jl * chunk:(jl + 1) * chunk], chunk, own))

@@ -27,6 +27,7 @@ SIGNATURES = {
     "gpb200_create": (C.c_int, [C.POINTER(_h), C.c_int]),
     "gpb200_destroy": (C.c_int, [_h]),
     "gpb200_set_stream": (C.c_int, [_h, C.c_void_p]),
+    "gpb200_set_stream_unordered": (C.c_int, [_h, C.c_void_p]),
     "gpb200_set_pointer_mode": (C.c_int, [_h, C.c_int]),
     "gpb200_synchronize": (C.c_int, [_h]),
     "gpb200_last_error": (C.c_char_p, [_h]),
@@ -88,6 +89,8 @@ SIGNATURES = {
     "gpb200_mg_panel_factor_col": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_int, C.c_void_p]),
     "gpb200_mg_panel_update": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_int, C.c_int, C.c_void_p,
                                          _ll]),
+    "gpb200_mg_panel_update_cols": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_int, C.c_int, C.c_void_p,
+                                              _ll, C.c_int, C.c_int]),
     "gpb200_mg_panel_trsv": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_void_p, _ll, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "gpb200_mg_comm_id": (C.c_int, [_h, C.c_void_p]),
@@ -185,8 +188,10 @@ class Handle:
             raise NotPositiveDefiniteError(where, rc)
         return rc
 
-    def set_stream(self, cuda_stream_ptr):
-        self._check(self.lib.gpb200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+    def set_stream(self, cuda_stream_ptr, ordered=True):
+        """ordered=False: no edge from the old stream to the new one (the caller orders with its own events)"""
+        f = self.lib.gpb200_set_stream if ordered else self.lib.gpb200_set_stream_unordered
+        self._check(f(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
 
     def set_pointer_mode(self, device: bool):
         self._check(self.lib.gpb200_set_pointer_mode(self._h, int(bool(device))), "set_pointer_mode")

@@ -105,6 +105,14 @@ extern "C" int gpb200_set_stream(gpb200_handle_t h, void *s) {
   }
   return 0;
 }
+// The same without the ordering edge, for callers that run independent work of ONE handle on several streams and order
+// it with their own events (the block-cyclic schedule: panel chain, side updates and trailing updates overlap).  Only the
+// entry points that touch no handle-owned scratch may be used this way (gpb200_mg_panel_*, gpb200_mg_bcast / _wait).
+extern "C" int gpb200_set_stream_unordered(gpb200_handle_t h, void *s) {
+  CHECK_H(h);
+  h->stream = reinterpret_cast<cudaStream_t>(s);
+  return 0;
+}
 extern "C" int gpb200_set_pointer_mode(gpb200_handle_t h, int dev) {
   if (!h) return -1;
   h->device_ptrs = dev ? 1 : 0;

@@ -224,24 +224,33 @@ extern "C" int gpb200_mg_panel_factor_col(gpb200_handle_t h, int n, int col0, in
   return mg_factor_col(h, n, col0, ncols, P, ldp, jl, info_dev);
 }
 
-extern "C" int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P, long long ldp,
-                                      int ccol0, int cncols, double *Cp, long long ldc) {
+// Apply a factored panel to tile columns [jl0, jl1) of a panel right of it: C -= P_rows * P_cols^T (NT, K = pncols).
+// The column range lets the owner of the next panel update its first tile column alone on the panel chain and the other
+// ones beside the chain (block_cyclic.py::_factor_native).
+extern "C" int gpb200_mg_panel_update_cols(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P, long long ldp,
+                                           int ccol0, int cncols, double *Cp, long long ldc, int jl0, int jl1) {
   CHECK_H(h);
   int np;
   RC(mg_check_panel(h, n, pcol0, pncols, ldp, &np));
   RC(mg_check_panel(h, n, ccol0, cncols, ldc, &np));
   if (ccol0 < pcol0 + pncols) BAD_ARG(h, 7, "mg_panel_update: the target panel must lie right of the source panel");
   const int nt = np / TILE, d = (ccol0 - pcol0) / TILE, cnt = cncols / TILE, crt = nt - ccol0 / TILE, pk = pncols / TILE;
+  if (jl0 < 0 || jl1 > cnt || jl0 >= jl1) BAD_ARG(h, 11, "mg_panel_update_cols: empty or out-of-range tile-column range");
   TaskList tl;
   const long long key = mgkey(TK_MG_UPDATE, d, cnt, crt, pk);
   if (!cached(h, key, &tl)) {
     std::vector<TileTask> t;
-    for (int jl = 0; jl < cnt; jl++)
+    std::vector<int> off(1, 0);
+    for (int jl = 0; jl < cnt; jl++) {
       for (int il = jl; il < crt; il++)  // il, jl: tile coordinates local to the target panel
         t.push_back({(il + d) * TILE, 0, (jl + d) * TILE, 0, il * TILE, jl * TILE, pk * TILE, il == jl});
-    std::vector<int> off = {0, (int)t.size()};
+      off.push_back((int)t.size());
+    }
     RC(upload_tasks(h, key, t, off, &tl));
   }
+  int ntasks = 0;
+  for (int jl = jl0; jl < jl1; jl++) ntasks += tl.count(jl);
+  if (ntasks == 0) return 0;
   GemmParams p{};
   p.A = mref(const_cast<double *>(P), ldp, 0);
   p.B = mref(const_cast<double *>(P), ldp, 0);
@@ -249,8 +258,13 @@ extern "C" int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int p
   p.C0 = mref(Cp, ldc, 0);
   p.alpha = -1.0;
   p.beta = 1.0;
-  p.tasks = tl.at(0);
-  return launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(0), 1);
+  p.tasks = tl.at(jl0);
+  return launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, ntasks, 1);
+}
+
+extern "C" int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P, long long ldp,
+                                      int ccol0, int cncols, double *Cp, long long ldc) {
+  return gpb200_mg_panel_update_cols(h, n, pcol0, pncols, P, ldp, ccol0, cncols, Cp, ldc, 0, cncols / TILE);
 }
 
 // forward substitution through one factored panel: z[pcol0 .. +ncols) = solve, acc[rows below] +=

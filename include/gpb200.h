@@ -39,6 +39,10 @@ typedef struct gpb200_handle_s *gpb200_handle_t;
 GPB200_API int gpb200_create(gpb200_handle_t *h, int device);          /* one handle per GPU / host thread  */
 GPB200_API int gpb200_destroy(gpb200_handle_t h);
 GPB200_API int gpb200_set_stream(gpb200_handle_t h, void *cuda_stream); /* cudaStream_t; NULL = default      */
+/* gpb200_set_stream orders the new stream after everything the handle enqueued on the old one (one workspace per handle).
+ * The _unordered form adds no such edge: for callers that overlap independent gpb200_mg_panel_* / gpb200_mg_bcast work of
+ * one handle on several streams and order it with their own events (gp_b200/block_cyclic.py). */
+GPB200_API int gpb200_set_stream_unordered(gpb200_handle_t h, void *cuda_stream);
 GPB200_API int gpb200_set_pointer_mode(gpb200_handle_t h, int device_pointers);
 GPB200_API int gpb200_synchronize(gpb200_handle_t h);
 GPB200_API const char *gpb200_last_error(gpb200_handle_t h);
@@ -258,6 +262,10 @@ GPB200_API int gpb200_mg_panel_factor_col(gpb200_handle_t h, int n, int col0, in
 /* right-looking update of a panel to the right: C -= P(rows of C) P(cols of C)^T, lower part */
 GPB200_API int gpb200_mg_panel_update(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P,
                                       long long ldp, int ccol0, int cncols, double *C, long long ldc);
+/* the same restricted to tile columns [jl0, jl1) of the target panel */
+GPB200_API int gpb200_mg_panel_update_cols(gpb200_handle_t h, int n, int pcol0, int pncols, const double *P,
+                                           long long ldp, int ccol0, int cncols, double *C, long long ldc, int jl0,
+                                           int jl1);
 /* forward substitution through a factored panel: z[col0..] solved, acc[below] += L z;
  * y, acc, z: length-np device vectors; wscratch: ldp x 128 doubles */
 GPB200_API int gpb200_mg_panel_trsv(gpb200_handle_t h, int n, int col0, int ncols, const double *P,

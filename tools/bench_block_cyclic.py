@@ -1,7 +1,7 @@
 """SURVEY config 5: ONE large exact GP, N = 4k..32k, block-column-cyclic Cholesky over the GPUs of one box with the
 panel broadcasts enqueued from C (ncclBroadcast through gpb200_mg_bcast), then the exact distributed gradient.
 Launch with torchrun (or plain python for one GPU):
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 tools/bench_block_cyclic.py [N ...] [--panel=512]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 tools/bench_block_cyclic.py [N ...] [--panel=512] [--combos=n:panel_cols:split,...]
 One JSON line per N on rank 0: factorisation and LML+gradient times (CUDA events, max over ranks), TFLOP/s on N^3/3 and N^3,
 fraction of P x the measured FP64 peak, and the relative difference from the single-GPU path of the same library (rank 0)."""
 import json
@@ -19,12 +19,12 @@ from gp_b200.block_cyclic import BlockCyclicGP, GpuPanelBackend  # noqa: E402
 PEAK = 37.03
 
 
-def run_one(n, pc, be, h, dev, world, rank, reps=3, check_single=True):
+def run_one(n, pc, be, h, dev, world, rank, reps=3, check_single=True, split_update=None):
     rng = np.random.default_rng(5)
     x = np.sort(rng.uniform(0, 0.05 * n, n))
     y = np.sin(x) + 0.5 * np.sin(3.1 * x) + 0.3 * rng.standard_normal(n)
     theta = (1.0, 1.0, 0.3)
-    bc = BlockCyclicGP(n, panel_cols=pc, backend=be, keep_all=True)
+    bc = BlockCyclicGP(n, panel_cols=pc, backend=be, keep_all=True, split_update=split_update)
     bc.factor(x, *theta)          # warm-up (task lists, NCCL channels)
     bc.lml_grad(y)
 
@@ -50,7 +50,7 @@ def run_one(n, pc, be, h, dev, world, rank, reps=3, check_single=True):
            "ms": round(best_f + best_g, 3), "chol_tflops": round(n ** 3 / 3.0 / best_f * 1e-9, 2),
            "tflops": round(float(n) ** 3 / (best_f + best_g) * 1e-9, 2),
            "frac": round(float(n) ** 3 / (best_f + best_g) * 1e-9 / (world * PEAK), 4), "lml": val, "grad": [float(g) for g in grad],
-           "grad_full": [float(g) for g in grad], "info": info}
+           "grad_full": [float(g) for g in grad], "info": info, "split_update": bool(bc.split_update)}
     del bc
     torch.cuda.empty_cache()
     if check_single and rank == 0 and n <= 32768:
@@ -76,8 +76,13 @@ def main():
     h = capi.Handle(local)
     be = GpuPanelBackend(h, dev).init_comm()
     out = []
-    for n in sizes:
-        rec, _ = run_one(n, pc, be, h, dev, world, rank)
+    combos = [(n, pc, None) for n in sizes]
+    for a in sys.argv[1:]:
+        if a.startswith("--combos="):       # n:panel_cols:split_update, ... -- a sweep inside one process group
+            combos = [tuple(int(v) for v in c.split(":")) for c in a.split("=")[1].split(",")]
+    for n, pc, sp in combos:
+        rec, _ = run_one(n, pc, be, h, dev, world, rank, split_update=None if sp is None else bool(sp),
+                         check_single=sp is None)
         rec.pop("grad_full", None)
         out.append(rec)
         if rank == 0:
