@@ -26,6 +26,7 @@ void free_handle(gpb200_handle_s *h) {
   if (h->ws) cudaFree(h->ws);
   if (h->latent_L) cudaFree(h->latent_L);
   if (h->info_slot) cudaFree(h->info_slot);
+  if (h->panel_flags) cudaFree(h->panel_flags);
   for (auto &kv : h->task_cache) cudaFree(kv.second.first);
   for (auto &kv : h->split_cache) if (kv.second.reg) cudaFree(kv.second.reg);
   delete h;
@@ -53,7 +54,9 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
       cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->stream_switch, cudaEventDisableTiming) != cudaSuccess ||
-      cudaMalloc(&h->info_slot, sizeof(int)) != cudaSuccess) { free_handle(h); return -1000; }
+      cudaMalloc(&h->info_slot, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&h->panel_flags, 2 * PANEL_FUSED_MAX_BATCH * sizeof(int)) != cudaSuccess ||
+      cudaMemset(h->panel_flags, 0, 2 * PANEL_FUSED_MAX_BATCH * sizeof(int)) != cudaSuccess) { free_handle(h); return -1000; }
   {
     int lo = 0, hi = 0;  // numerically lowest value = highest priority
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
@@ -79,6 +82,8 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (ds && ds[0] == '0') h->diag_split = 0;
   const char *tm = getenv("GPB200_TRSM_MT");
   if (tm && (tm[0] == '1' || tm[0] == '2')) h->trsm_mt_override = tm[0] - '0';
+  const char *pf = getenv("GPB200_PANEL_FUSED");
+  if (pf && pf[0] == '0') h->panel_fused = 0;
   const char *ng = getenv("GPB200_NO_GRAPH");
   if (ng && ng[0] == '1') h->graphs_enabled = 0;
   *out = h;
@@ -516,11 +521,12 @@ extern "C" int gpb200_mvn_chol_lpdf(gpb200_handle_t h, int n, const double *y, c
 //   what = 0  POTRF of the first diagonal tile           (1 CTA per item)
 //   what = 1  TRSM of the nt-1 tiles below it             (after the POTRF)
 //   what = 2  inverse of the nt diagonal tiles            (after a full factorisation)
+//   what = 3  POTRF + TRSM of the first block column      (one fused launch where that applies, else the two launches)
 // ms_out[0] = mean kernel time in ms.  DEVICE work only; not part of the reference-facing surface.
 // =================================================================================================
 extern "C" int gpb200_debug_bench_panel(gpb200_handle_t h, int what, int nt, int batch, int reps, double *ms_out) {
   CHECK_H(h);
-  if (nt < 1 || batch < 1 || reps < 1 || what < 0 || what > 2) BAD_ARG(h, 2, "debug_bench_panel: bad arguments");
+  if (nt < 1 || batch < 1 || reps < 1 || what < 0 || what > 3) BAD_ARG(h, 2, "debug_bench_panel: bad arguments");
   const int np = nt * TILE, n = np;
   const long long mat = (long long)np * np;
   Arena a;
@@ -542,12 +548,13 @@ extern "C" int gpb200_debug_bench_panel(gpb200_handle_t h, int what, int nt, int
   int rc = 0;
   for (int r = 0; r < reps + 1 && !rc; r++) {  // repetition 0 is a warm-up
     rc = launch_gram_se_batched(h, n, np, dx, 0, dth, 0.0, 1, Lbuf, mat, batch);
-    if (!rc && what >= 1) rc = launch_potrf_tile(h, Lbuf, np, mat, 0, n, batch, info);
+    if (!rc && (what == 1 || what == 2)) rc = launch_potrf_tile(h, Lbuf, np, mat, 0, n, batch, info);
     if (!rc && what == 2) rc = chol_batched(h, Lbuf, np, mat, n, batch, info);
     if (rc) break;
     cudaEventRecord(e0, h->stream);
     if (what == 0) rc = launch_potrf_tile(h, Lbuf, np, mat, 0, n, batch, info);
     else if (what == 1) rc = launch_trsm_tiles(h, Lbuf, np, mat, 0, nt - 1, batch);
+    else if (what == 3) rc = launch_potrf_trsm(h, Lbuf, np, mat, 0, nt - 1, n, batch, info);
     else rc = launch_tile_inverse(h, Lbuf, Wbuf, np, mat, nt, batch);
     cudaEventRecord(e1, h->stream);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = -1000;

@@ -199,8 +199,7 @@ int mg_factor_col(Handle *h, int n, int col0, int ncols, double *P, long long ld
     RC(launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(jl), 1));
   }
   const long long doff = (long long)jl * TILE * (ldp + 1);
-  RC(launch_potrf_tile_at(h, P, ldp, 0, doff, col0 + jl * TILE, n, 1, info_dev));
-  return launch_trsm_tiles_at(h, P, ldp, 0, doff, doff + TILE, nrt - 1 - jl, 1);
+  return launch_potrf_trsm_at(h, P, ldp, 0, doff, col0 + jl * TILE, n, doff + TILE, nrt - 1 - jl, 1, info_dev);
 }
 }  // namespace
 

@@ -9,6 +9,7 @@
 
 namespace gpb {
 
+constexpr int PANEL_FUSED_MAX_BATCH = 148;  // matrices per panel_fused_kernel launch (flag slots in the handle)
 constexpr int TILE = 128;  // tile edge of every tiled algorithm (internal matrices are padded to it)
 
 inline int round_up(int n, int m) { return (n + m - 1) / m * m; }
@@ -73,6 +74,8 @@ struct Handle {
   int trsm_pipelined = 1;     // 0: one tile per CTA (the first TRSM tile kernel); env GPB200_TRSM_PIPELINED
   int panel_impl = 0;         // 0: round-2 shared-memory panel kernels (POTRF with a panel warp); 1: the round-1 register-tile kernels; 2: round-2 POTRF without the panel warp (env GPB200_PANEL_V1 = 1 | 2)
   int trsm_mt_override = 0;   // tuning knob: 8-row mma tiles per warp of trsm_ll_kernel (1, 2, 4); env GPB200_TRSM_MT
+  int panel_fused = 1;        // POTRF tile and the TRSM below it in one launch when one wave holds both (panel_fused_kernel); env GPB200_PANEL_FUSED
+  int *panel_flags = nullptr; // 2 ints per matrix for panel_fused_kernel (visible column blocks, finished TRSM CTAs), zero between launches
   char err[512] = {0};
   // grow-only device workspace
   void *ws = nullptr;
@@ -204,6 +207,12 @@ int launch_potrf_tile_at(Handle *h, double *L, long long ld, long long stride, l
                          int n, int batch, int *info);
 int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, long long c_off,
                          int ntiles, int batch);
+// POTRF of the diagonal tile at diag_off, then TRSM of the `ntiles` tiles from c_off down: one fused launch on the
+// latency path, otherwise the two launches above
+int launch_potrf_trsm_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, int index_base, int n,
+                         long long c_off, int ntiles, int batch, int *info);
+int launch_potrf_trsm(Handle *h, double *L, long long ld, long long stride, int tile_col, int ntiles_below, int n, int batch,
+                      int *info);
 int launch_tile_inverse_at(Handle *h, const double *L, long long ld, long long l_off, long long l_step, double *W,
                            long long w_off, long long w_step, long long stride, int ntiles, int batch);
 int panel_smem_setup(Handle *h);

@@ -241,8 +241,7 @@ static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int
         p.tasks = tl.at(j);
         if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(j), batch))) return rc;
       }
-      if ((rc = launch_potrf_tile(h, Lbuf, np, stride, j, n, batch, info_dev))) return rc;
-      if ((rc = launch_trsm_tiles(h, Lbuf, np, stride, j, nt - 1 - j, batch))) return rc;
+      if ((rc = launch_potrf_trsm(h, Lbuf, np, stride, j, nt - 1 - j, n, batch, info_dev))) return rc;
     }
     cudaEvent_t ev_panel = h->sync_event(ev++);
     GPB_CUDA(h, cudaEventRecord(ev_panel, P));
@@ -283,9 +282,7 @@ int chol_batched(Handle *h, double *Lbuf, int np, long long stride, int n, int b
       rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(j), batch);
       if (rc) return rc;
     }
-    rc = launch_potrf_tile(h, Lbuf, np, stride, j, n, batch, info_dev);
-    if (rc) return rc;
-    rc = launch_trsm_tiles(h, Lbuf, np, stride, j, nt - 1 - j, batch);
+    rc = launch_potrf_trsm(h, Lbuf, np, stride, j, nt - 1 - j, n, batch, info_dev);
     if (rc) return rc;
     if ((j + 1) % pt == 0 && j + 1 < nt) {
       const int panel = j / pt;

@@ -434,16 +434,20 @@ constexpr int LD_T = TILE + 4;  // column-major tile in shared memory, 132: conf
 #ifdef GPB_PANEL_TRACE
 __device__ long long g_panel_trace[2048];
 #define PTRACE(cond, idx) do { if ((cond) && blockIdx.x == 0 && lane == 0) g_panel_trace[(idx)] = clock64(); } while (0)
+#define PTRACE_LAST(cond, idx) do { if ((cond) && blockIdx.x == gridDim.x - 1 && (threadIdx.x & 31) == 0) g_panel_trace[(idx)] = clock64(); } while (0)
 #else
 #define PTRACE(cond, idx) do { } while (0)
+#define PTRACE_LAST(cond, idx) do { } while (0)
 #endif
 constexpr int POTRF_PW_THREADS = 288;
 constexpr int POTRF_PW_SMEM_BYTES = (TILE * LD_T + 16 * 64 + 16 * 8 + 64) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(POTRF_PW_THREADS, 1)
-potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
-                     int n, int *info) {
-  extern __shared__ __align__(16) double sm[];
+// FOLLOWED = true (the diagonal CTAs of panel_fused_kernel): every finished column block goes to its final place in
+// global memory at once (instead of one write-back at the end) and *flag counts the column blocks that are visible
+// device-wide, so that the TRSM CTAs of the same launch can trail the factorisation by one block.
+template <bool FOLLOWED>
+__device__ __forceinline__ void potrf_pw_body(double *sm, double *__restrict__ T, long long ld, int index_base, int n,
+                                              int *info_slot, volatile int *pub_ready) {
   double *Ts = sm;                    // Ts[c * LD_T + r] = T[r][c]  (rows at / below the 8-block of c only)
   double *Dall = sm + TILE * LD_T;    // Dall[cb * 64 + c * 8 + cp] = L_D(cb)[c][cp], cp <= c (row-major), zero above
   double *Iall = Dall + 16 * 64;      // Iall[cb * 8 + c] = 1 / L_D(cb)[c][c]
@@ -452,8 +456,12 @@ potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const bool panel = warp == 8;
-  double *T = Lbase + (long long)blockIdx.x * stride + diag_off;
   if (tid == 0) s_info = 0;
+  // FOLLOWED: the CTA has a tenth warp (the publisher) that stays out of these barriers
+  auto step_sync = [] {
+    if (FOLLOWED) asm volatile("bar.sync 0, 288;\n" ::: "memory");
+    else __syncthreads();
+  };
   PTRACE(warp >= 7, (warp - 7) * 512 + 18 * 8 + 0);
 
   for (int idx = tid; idx < TILE * TILE / 2; idx += POTRF_PW_THREADS) {
@@ -466,7 +474,7 @@ potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride,
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   for (int idx = tid; idx < 16 * 64; idx += POTRF_PW_THREADS) Dall[idx] = 0.0;
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  __syncthreads();
+  step_sync();
 
   // factor the 8x8 block whose updated values sit in Dtmp[c * 8 + r] (column-major) and publish it as block `blk`
   auto factor_publish = [&](int blk) {
@@ -496,7 +504,7 @@ potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride,
     __syncwarp();
     factor_publish(0);
   }
-  __syncthreads();
+  step_sync();
 
   const int r0 = warp * 16;
   double ps[2][2];  // panel warp: running sum of L[c1.., k] L[c1.., k]^T for the NEXT diagonal block
@@ -533,8 +541,9 @@ potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride,
       }
     }
     PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 1);
-    __syncthreads();
+    step_sync();
     PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 2);
+    if (FOLLOWED && tid == 0) *pub_ready = cb + 1;   // column block cb is final: the publisher warp takes it from here
     if (cb == 15) break;
     // ---- phase 2 ----------------------------------------------------------------------------------------------
     if (!panel) {
@@ -573,13 +582,12 @@ potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride,
       factor_publish(cb + 1);
     }
     PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 4);
-    __syncthreads();
+    step_sync();
     PTRACE(warp >= 7, (warp - 7) * 512 + cb * 8 + 5);
   }
   PTRACE(warp >= 7, (warp - 7) * 512 + 16 * 8 + 0);
-
   // write back: lower triangle = L (diagonal blocks from Dall), strict upper = 0 (Eigen matrixL() convention)
-  for (int idx = tid; idx < TILE * TILE / 2; idx += POTRF_PW_THREADS) {
+  for (int idx = tid; !FOLLOWED && idx < TILE * TILE / 2; idx += POTRF_PW_THREADS) {
     const int c = idx >> 6, r = 2 * (idx & 63);
     double2 v = make_double2(0.0, 0.0);
     if ((r >> 3) == (c >> 3)) {
@@ -593,8 +601,52 @@ potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride,
   }
   PTRACE(warp >= 7, (warp - 7) * 512 + 16 * 8 + 1);
   if (tid == 0 && s_info != 0 && s_info <= n) {
-    if (info[blockIdx.x] == 0) info[blockIdx.x] = s_info;
+    if (*info_slot == 0) *info_slot = s_info;
   }
+}
+
+// The tenth warp of a diagonal CTA of panel_fused_kernel.  When column block cb is final in shared memory (pub_ready,
+// written after the barrier that ends its substitution) it stores the block to its final place in global memory
+// (zeros above the diagonal block, the diagonal block from Dall, the substituted rows from Ts; lane -> column lane / 4,
+// four consecutive rows out of every sixteen) and releases *flag = cb + 1.  The stores and above all the release
+// (a device-scope fence: about a thousand cycles) are as long as a phase of the factorisation; on a warp of its own
+// they are off the step barriers (done by an idle helper warp they added 300 to 600 cycles to every block step, traced).
+__device__ __forceinline__ void potrf_publisher(const double *sm, double *__restrict__ T, long long ld, int *flag,
+                                                volatile int *pub_ready) {
+  const double *Ts = sm, *Dall = sm + TILE * LD_T;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int cb = 0; cb < 16; cb++) {
+    while (*pub_ready < cb + 1) __nanosleep(40);
+    __syncwarp();
+    __threadfence_block();
+    const int c = 8 * cb + (lane >> 2);
+    const double *o = Dall + cb * 64 + (c & 7);
+    double *dst = T + (long long)c * ld;
+#pragma unroll 2
+    for (int k = 0; k < 8; k++) {
+      const int rr = 16 * k + 4 * (lane & 3);
+      double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+      if (rr >= 8 * cb + 8) {
+        v0 = *reinterpret_cast<const double2 *>(Ts + c * LD_T + rr);
+        v1 = *reinterpret_cast<const double2 *>(Ts + c * LD_T + rr + 2);
+      } else if (rr >= 8 * cb) {
+        v0 = make_double2(o[(rr & 7) * 8], o[((rr + 1) & 7) * 8]);
+        v1 = make_double2(o[((rr + 2) & 7) * 8], o[((rr + 3) & 7) * 8]);
+      }
+      *reinterpret_cast<double2 *>(dst + rr) = v0;
+      *reinterpret_cast<double2 *>(dst + rr + 2) = v1;
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(flag), "r"(cb + 1) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(POTRF_PW_THREADS, 1)
+potrf_tile_pw_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, int index_base,
+                     int n, int *info) {
+  extern __shared__ __align__(16) double sm[];
+  potrf_pw_body<false>(sm, Lbase + (long long)blockIdx.x * stride + diag_off, ld, index_base, n, info + blockIdx.x, nullptr);
 }
 
 // X L^T = C for ROWS = 32 MT consecutive rows of a block column (MODE-0 semantics of trsm_tile_kernel), four warps
@@ -608,56 +660,65 @@ struct TrsmLL {
   static constexpr int SMEM_BYTES = (TILE * LD_T + 16 * 64 + TILE + TILE * LD_C) * (int)sizeof(double);
 };
 
-template <int MT>
-__global__ void __launch_bounds__(128)
-trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long stride, long long diag_off, long long c_off) {
+// FOLLOW = true (the TRSM CTAs of panel_fused_kernel): the diagonal tile is still being factored by another CTA of the
+// same launch; column block cb of L is fetched from global memory when *flag says it is visible (>= cb + 1).  The 128
+// working threads meet at named barrier 1 (the CTA has more threads than this role uses).
+template <int MT, bool FOLLOW>
+__device__ __forceinline__ void trsm_ll_body(double *sm, const double *Ld, double *Ct, long long ld, unsigned long long *ready) {
   constexpr int ROWS = TrsmLL<MT>::ROWS, LD_C = TrsmLL<MT>::LD_C;
-  extern __shared__ __align__(16) double sm[];
   double *Ls = sm;                   // Ls[k * LD_T + n] = L[n][k]
   double *Dall = sm + TILE * LD_T;   // Dall[cb * 64 + c * 8 + cp] = L[8cb + c][8cb + cp]
   double *invd = Dall + 16 * 64;     // 1 / L[n][n]
   double *Cs = invd + TILE;          // Cs[c * LD_C + r] = C[r][c]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const double *Ld = Ldiag_base + (long long)blockIdx.y * stride + diag_off;
-  double *Ct = Cbase + (long long)blockIdx.y * stride + c_off + (long long)blockIdx.x * ROWS;
+  auto role_sync = [] { asm volatile("bar.sync 1, 128;\n" ::: "memory"); };
 
   auto cp16 = [](double *dst, const double *src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
   };
-  PTRACE(warp == 0, 1024 + 18 * 8);
-  for (int idx = tid; idx < TILE * TILE / 2; idx += 128) {
-    const int k = idx >> 6, r2 = idx & 63;
-    if (2 * r2 + 1 >= (k & ~7)) cp16(Ls + k * LD_T + 2 * r2, Ld + 2 * r2 + (long long)k * ld);  // rows at / below the block row of k
+  if (FOLLOW) PTRACE_LAST(warp == 0, 1024 + 18 * 8); else PTRACE(warp == 0, 1024 + 18 * 8);
+  if (!FOLLOW) {
+    for (int idx = tid; idx < TILE * TILE / 2; idx += 128) {
+      const int k = idx >> 6, r2 = idx & 63;
+      if (2 * r2 + 1 >= (k & ~7)) cp16(Ls + k * LD_T + 2 * r2, Ld + 2 * r2 + (long long)k * ld);  // rows at / below the block row of k
+    }
   }
   for (int idx = tid; idx < TILE * ROWS / 2; idx += 128) {
     const int c = idx / (ROWS / 2), r2 = idx - c * (ROWS / 2);
     cp16(Cs + c * LD_C + 2 * r2, Ct + 2 * r2 + (long long)c * ld);
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  __syncthreads();
-  if (tid < TILE) invd[tid] = 1.0 / Ls[tid * LD_T + tid];
-  for (int idx = tid; idx < 16 * 64; idx += 128) {
-    const int cb = idx >> 6, c = (idx >> 3) & 7, cp = idx & 7;
-    Dall[idx] = Ls[(8 * cb + cp) * LD_T + 8 * cb + c];
+  if (!FOLLOW) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    role_sync();
+    if (tid < TILE) invd[tid] = 1.0 / Ls[tid * LD_T + tid];
+    for (int idx = tid; idx < 16 * 64; idx += 128) {
+      const int cb = idx >> 6, c = (idx >> 3) & 7, cp = idx & 7;
+      Dall[idx] = Ls[(8 * cb + cp) * LD_T + 8 * cb + c];
+    }
+    role_sync();
   }
-  __syncthreads();
 
   const int r0 = warp * 8 * MT;
   bool act[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) act[mt] = true;
-  PTRACE(warp == 0, 1024 + 17 * 8);
+  if (FOLLOW) PTRACE_LAST(warp == 0, 1024 + 17 * 8); else PTRACE(warp == 0, 1024 + 17 * 8);
+  if (FOLLOW) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    role_sync();   // the C chunk has landed for everybody
+  }
 #pragma unroll 1
   for (int cb = 0; cb < 16; cb++) {
     const int c0 = 8 * cb;
-    PTRACE(warp == 0, 1024 + cb * 8 + 0);
+    if (FOLLOW) PTRACE_LAST(warp == 0, 1024 + cb * 8 + 0); else PTRACE(warp == 0, 1024 + cb * 8 + 0);
     double dl[8][8], inv[8];
-    load_block8(Dall + cb * 64, invd + c0, dl, inv);   // fetched before the DMMA loop: landed long before the substitution
+    if (!FOLLOW) load_block8(Dall + cb * 64, invd + c0, dl, inv);   // fetched before the DMMA loop: landed long before the substitution
     if (cb > 0) {
-      // S = X[rows, 0:c0] * L[c0:c0+8, 0:c0]^T, two independent accumulation chains per m-tile
+      // S = X[rows, 0:c0] * L[c0:c0+8, 0:c0]^T, two independent accumulation chains per m-tile.  (FOLLOW: this part needs
+      // only column blocks < cb, which arrived one step ago: it runs BEFORE the wait for block cb.)
       double s[MT][2][2];
 #pragma unroll
       for (int mt = 0; mt < MT; mt++)
@@ -673,7 +734,26 @@ trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long 
         }
       __syncwarp();
     }
-    PTRACE(warp == 0, 1024 + cb * 8 + 1);
+    if (FOLLOW) {
+      PTRACE_LAST(warp == 0, 1024 + cb * 8 + 3);
+      // column block cb is staged by the loader warp (trsm_follow_loader) while these warps do the update above
+      {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(ready + cb);
+        asm volatile(
+            "{\n.reg .pred p;\nWAIT_BLOCK:\n"
+            "mbarrier.try_wait.parity.shared.b64 p, [%0], 0;\n"
+            "@!p bra WAIT_BLOCK;\n}\n" ::"r"(mb) : "memory");
+      }
+      // every lane reads the 8x8 diagonal block straight from the staged columns (lower part; the upper part is zero)
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int cp = 0; cp < 8; cp++) dl[c][cp] = cp < c ? Ls[(c0 + cp) * LD_T + c0 + c] : 0.0;
+      const double my_inv = 1.0 / Ls[(c0 + (lane & 7)) * (LD_T + 1)];   // one reciprocal per lane, handed round
+#pragma unroll
+      for (int c = 0; c < 8; c++) inv[c] = __shfl_sync(0xffffffffu, my_inv, c);
+    }
+    if (FOLLOW) PTRACE_LAST(warp == 0, 1024 + cb * 8 + 1); else PTRACE(warp == 0, 1024 + cb * 8 + 1);
     // substitution against the 8x8 diagonal block, one row per lane
     if (lane < 8 * MT) {
       double *px = Cs + c0 * LD_C + r0 + lane;
@@ -683,15 +763,119 @@ trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long 
       solve_row8(x, dl, inv);
 #pragma unroll
       for (int c = 0; c < 8; c++) px[c * LD_C] = x[c];
+      if (FOLLOW) {   // finished columns go out at once: nothing is left to write when the last block has been solved
+        double *out = Ct + r0 + lane + (long long)c0 * ld;
+#pragma unroll
+        for (int c = 0; c < 8; c++) out[(long long)c * ld] = x[c];
+      }
     }
     __syncwarp();
-    PTRACE(warp == 0, 1024 + cb * 8 + 2);
+    if (FOLLOW) PTRACE_LAST(warp == 0, 1024 + cb * 8 + 2); else PTRACE(warp == 0, 1024 + cb * 8 + 2);
   }
-  __syncthreads();
+  if (FOLLOW) { PTRACE_LAST(warp == 0, 1024 + 16 * 8); return; }
+  role_sync();
   PTRACE(warp == 0, 1024 + 16 * 8);
   for (int idx = tid; idx < TILE * ROWS / 2; idx += 128) {
     const int c = idx / (ROWS / 2), r2 = idx - c * (ROWS / 2);
     *reinterpret_cast<double2 *>(Ct + 2 * r2 + (long long)c * ld) = *reinterpret_cast<const double2 *>(Cs + c * LD_C + 2 * r2);
+  }
+}
+
+// The fifth warp of a TRSM CTA of panel_fused_kernel: waits for each column block of the diagonal tile to become visible
+// (*flag >= cb + 1, raised by the diagonal CTA) and copies its rows at and below the diagonal block into the CTA's staged L
+// with cp.async; the copies of block cb complete on mbarrier ready[cb] (one arrival per lane, counted when that lane's
+// copies have landed), which is what the four working warps wait on -- so the L2 round trips of the wait and of the copy
+// run beside the working warps' DMMA updates, and this warp is already polling for block cb + 1 while block cb lands.
+__device__ __forceinline__ void trsm_follow_loader(double *sm, const double *Ld, long long ld, const int *flag,
+                                                   unsigned long long *ready) {
+  double *Ls = sm;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int cb = 0; cb < 16; cb++) {
+    const int c0 = 8 * cb;
+    PTRACE_LAST(true, 1536 + cb * 8 + 0);
+    if (lane == 0) {
+      int seen;
+      do {   // relaxed polls (an acquire load invalidates the L1 on every iteration), one acquire fence at the end
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(flag) : "memory");
+      } while (seen < cb + 1);
+      asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+    }
+    __syncwarp();
+    PTRACE_LAST(true, 1536 + cb * 8 + 1);
+    // all 128 rows of the eight columns (the rows above the diagonal block are zeros nobody reads): a fixed pattern of
+    // sixteen 16-byte copies per lane keeps this loop a few dozen instructions long
+    {
+      const double *src = Ld + (long long)c0 * ld + 2 * lane;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(Ls + c0 * LD_T + 2 * lane);
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (unsigned)(c * LD_T * 8)), "l"(src + (long long)c * ld) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (unsigned)(c * LD_T * 8 + 512)), "l"(src + (long long)c * ld + 64) : "memory");
+      }
+    }
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(ready + cb);
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(mb) : "memory");
+    PTRACE_LAST(true, 1536 + cb * 8 + 2);
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");   // nothing of this warp is in flight when it exits
+}
+
+template <int MT>
+__global__ void __launch_bounds__(128)
+trsm_ll_kernel(const double *Ldiag_base, double *Cbase, long long ld, long long stride, long long diag_off, long long c_off) {
+  extern __shared__ __align__(16) double sm[];
+  trsm_ll_body<MT, false>(sm, Ldiag_base + (long long)blockIdx.y * stride + diag_off,
+                          Cbase + (long long)blockIdx.y * stride + c_off + (long long)blockIdx.x * TrsmLL<MT>::ROWS, ld, nullptr);
+}
+
+// POTRF of the diagonal tile and the TRSM of the tiles below it in ONE launch (the latency path: one or a few matrices).
+// CTAs [0, batch) factor the diagonal tiles and publish them column block by column block; CTAs [batch, ...) take
+// 32 MT rows each of the block column below and trail the factorisation by about one 8-column block instead of
+// starting when it has finished (16.5 us later and a launch gap).  The diagonal CTAs wait for nobody and have the
+// lowest block indices, so every waiting CTA waits for a CTA that is already resident.  flags[2 m] counts matrix m's
+// visible column blocks, flags[2 m + 1] its finished TRSM CTAs; the last one to finish clears both for the next launch.
+template <int MT>
+struct PanelFused {
+  static constexpr int SMEM_BYTES = TrsmLL<MT>::SMEM_BYTES > POTRF_PW_SMEM_BYTES ? TrsmLL<MT>::SMEM_BYTES : POTRF_PW_SMEM_BYTES;
+};
+
+constexpr int PANEL_FUSED_THREADS = POTRF_PW_THREADS + 32;
+
+template <int MT>
+__global__ void __launch_bounds__(PANEL_FUSED_THREADS, 1)
+panel_fused_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, long long c_off,
+                   int chunks, int batch, int index_base, int n, int *info, int *flags) {
+  extern __shared__ __align__(16) double sm[];
+  if ((int)blockIdx.x < batch) {
+    __shared__ int s_pub;
+    const int m = blockIdx.x;
+    double *T = Lbase + (long long)m * stride + diag_off;
+    if (threadIdx.x == POTRF_PW_THREADS) s_pub = 0;
+    __syncthreads();
+    if (threadIdx.x >= POTRF_PW_THREADS) potrf_publisher(sm, T, ld, flags + 2 * m, &s_pub);
+    else potrf_pw_body<true>(sm, T, ld, index_base, n, info + m, &s_pub);
+    return;
+  }
+  __shared__ __align__(8) unsigned long long s_ready[16];   // one mbarrier per column block, each used for one phase
+  if (threadIdx.x >= 160) return;
+  const int idx = (int)blockIdx.x - batch, m = idx / chunks, chunk = idx - m * chunks;
+  double *base = Lbase + (long long)m * stride;
+  if (threadIdx.x >= 128 && threadIdx.x < 144) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(s_ready + (threadIdx.x - 128));
+    asm volatile("mbarrier.init.shared.b64 [%0], 32;\n" ::"r"(mb) : "memory");
+  }
+  asm volatile("bar.sync 2, 160;\n" ::: "memory");
+  if (threadIdx.x >= 128) {
+    trsm_follow_loader(sm, base + diag_off, ld, flags + 2 * m, s_ready);
+    return;
+  }
+  trsm_ll_body<MT, true>(sm, base + diag_off, base + c_off + (long long)chunk * TrsmLL<MT>::ROWS, ld, s_ready);
+  if (threadIdx.x == 0) {
+    if (atomicAdd(flags + 2 * m + 1, 1) == chunks - 1) {
+      flags[2 * m + 1] = 0;
+      *reinterpret_cast<volatile int *>(flags + 2 * m) = 0;
+    }
   }
 }
 
@@ -804,6 +988,8 @@ int panel_smem_setup(Handle *h) {
   GPB_CUDA(h, cudaFuncSetAttribute(potrf_tile_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_PW_SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<1>::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<2>::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(panel_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PanelFused<1>::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(panel_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PanelFused<2>::SMEM_BYTES));
   return 0;
 }
 
@@ -860,6 +1046,38 @@ int launch_trsm_tiles_at(Handle *h, double *L, long long ld, long long stride, l
 int launch_trsm_tiles(Handle *h, double *L, long long ld, long long stride, int tile_col, int ntiles_below, int batch) {
   return launch_trsm_tiles_at(h, L, ld, stride, (long long)tile_col * TILE * (ld + 1),
                               (long long)(tile_col + 1) * TILE + (long long)tile_col * TILE * ld, ntiles_below, batch);
+}
+
+int launch_potrf_trsm_at(Handle *h, double *L, long long ld, long long stride, long long diag_off, int index_base, int n,
+                         long long c_off, int ntiles, int batch, int *info) {
+  // one launch when the diagonal CTAs and the 64-row (or 32-row) TRSM CTAs of all matrices fit one wave at one CTA per SM
+  int mt = 0;
+  if (h->panel_fused && h->panel_impl == 0 && ntiles > 0 && batch <= PANEL_FUSED_MAX_BATCH) {
+    if (h->trsm_mt_override == 1 && (long long)batch * (1 + 4 * ntiles) <= 148) mt = 1;
+    else if ((long long)batch * (1 + 2 * ntiles) <= 148) mt = 2;
+  }
+  if (mt == 0) {
+    int rc = launch_potrf_tile_at(h, L, ld, stride, diag_off, index_base, n, batch, info);
+    if (rc) return rc;
+    return launch_trsm_tiles_at(h, L, ld, stride, diag_off, c_off, ntiles, batch);
+  }
+  ProfScope ps__(h, PC_POTRF);
+  const int chunks = ntiles * (4 / mt);
+  const int grid = batch * (1 + chunks);
+  if (mt == 1)
+    panel_fused_kernel<1><<<grid, PANEL_FUSED_THREADS, PanelFused<1>::SMEM_BYTES, h->stream>>>(L, ld, stride, diag_off, c_off, chunks,
+                                                                                          batch, index_base, n, info, h->panel_flags);
+  else
+    panel_fused_kernel<2><<<grid, PANEL_FUSED_THREADS, PanelFused<2>::SMEM_BYTES, h->stream>>>(L, ld, stride, diag_off, c_off, chunks,
+                                                                                          batch, index_base, n, info, h->panel_flags);
+  GPB_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int launch_potrf_trsm(Handle *h, double *L, long long ld, long long stride, int tile_col, int ntiles_below, int n, int batch,
+                      int *info) {
+  return launch_potrf_trsm_at(h, L, ld, stride, (long long)tile_col * TILE * (ld + 1), tile_col * TILE, n,
+                              (long long)(tile_col + 1) * TILE + (long long)tile_col * TILE * ld, ntiles_below, batch, info);
 }
 
 // inverse of `ntiles` diagonal tiles: L tiles at l_off + t*l_step, W tiles at w_off + t*w_step
