@@ -879,6 +879,206 @@ panel_fused_kernel(double *__restrict__ Lbase, long long ld, long long stride, l
   }
 }
 
+// ---- the TRSM CTAs of panel_fused_tile_kernel (more row tiles than 64-row CTAs fit in one wave) -------------------
+// One CTA per 128-row tile below the diagonal tile: eight working warps of sixteen rows each, one loader warp.  The
+// diagonal tile is still being factored by another CTA of the same launch, which publishes it column block by
+// column block (*flag = number of visible blocks).  Step cb of the substitution needs row block cb of L:
+//   part A  L[8cb .. 8cb+7][0 .. 8cb-1]   lies in column blocks < cb: visible one step EARLIER (flag >= cb)
+//   part D  the 8x8 diagonal block         visible when flag >= cb + 1
+// so the loader stages part A of row block i and part D of block i - 1 when the flag reaches i; the working warps do
+// the DMMA update of step cb (part A) while block cb is still on its way and wait only for its 64 diagonal-block
+// numbers.  Part A lives in two alternating buffers (full / empty mbarriers), part D in sixteen one-shot slots.
+// Only the C tile is resident (135 KB): a row tile per CTA, so one launch covers up to 147 row tiles.
+constexpr int LD_R = 20;   // row-block buffer RB[k * LD_R + i] = L[8cb + i][k]; 20 = 4 (mod 16): conflict-free B fragments
+template <int NW>   // working warps per CTA: 4 (64 rows) or 8 (128 rows)
+struct Follow {
+  static constexpr int ROWS = 16 * NW, LD_C = ROWS + 4;
+  static constexpr int C_DOUBLES = TILE * LD_C;
+  static constexpr int SMEM_BYTES = (C_DOUBLES + 2 * TILE * LD_R + 16 * 64) * (int)sizeof(double);
+};
+
+struct FollowBars {
+  unsigned long long fullD[16], fullR[2], emptyR[2];
+};
+
+__device__ __forceinline__ void mbar_wait(const unsigned long long *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_copies(unsigned long long *bar) {   // counted when this thread's cp.asyncs have landed
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(a) : "memory");
+}
+
+__device__ __forceinline__ void trsm_tile_follow_loader(double *RB, const double *Ld, long long ld, const int *flag, FollowBars *bars) {
+  double *Dbuf = RB + 2 * TILE * LD_R;
+  const int lane = threadIdx.x & 31;
+  const int part = lane & 3, colq = lane >> 2;
+#pragma unroll 1
+  for (int i = 1; i <= 16; i++) {
+    PTRACE_LAST(true, 1536 + (i - 1) * 8 + 0);
+    if (lane == 0) {
+      int seen;
+      do {   // relaxed polls (an acquire load invalidates the L1 on every iteration), one acquire fence at the end
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(flag) : "memory");
+      } while (seen < i);
+      asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+    }
+    __syncwarp();
+    PTRACE_LAST(true, 1536 + (i - 1) * 8 + 1);
+    {  // part D of block i - 1: 8 columns x 8 rows, one 16-byte piece per lane
+      const int d0 = 8 * (i - 1);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(Dbuf + (i - 1) * 64 + colq * 8 + 2 * part);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ld + d0 + 2 * part + (long long)(d0 + colq) * ld) : "memory");
+      mbar_arrive_on_copies(&bars->fullD[i - 1]);
+    }
+    if (i <= 15) {  // part A of row block i: rows 8i .. 8i+7 of columns 0 .. 8i-1
+      const int b = i & 1, use = (i - 1) >> 1;
+      if (use >= 1) mbar_wait(&bars->emptyR[b], (use - 1) & 1);
+      const double *src = Ld + 8 * i + 2 * part + (long long)colq * ld;
+      unsigned dst = (unsigned)__cvta_generic_to_shared(RB + b * TILE * LD_R + colq * LD_R + 2 * part);
+#pragma unroll 1
+      for (int col = colq; col < 8 * i; col += 8) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+        src += 8 * ld;
+        dst += 8 * LD_R * 8;
+      }
+      mbar_arrive_on_copies(&bars->fullR[b]);
+    }
+    PTRACE_LAST(true, 1536 + (i - 1) * 8 + 2);
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");   // nothing of this warp is in flight when it exits
+}
+
+template <int NW>
+__device__ __forceinline__ void trsm_tile_follow_compute(double *sm, double *Ct, long long ld, FollowBars *bars) {
+  constexpr int ROWS = Follow<NW>::ROWS, LD_C = Follow<NW>::LD_C;
+  double *Cs = sm;   // Cs[c * LD_C + r] = C[r][c], ROWS rows of the block column
+  const double *RB = sm + Follow<NW>::C_DOUBLES, *Dbuf = RB + 2 * TILE * LD_R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  PTRACE_LAST(warp == 0, 1024 + 18 * 8);
+  for (int idx = tid; idx < TILE * ROWS / 2; idx += 32 * NW) {
+    const int c = idx / (ROWS / 2), r2 = idx - c * (ROWS / 2);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(Cs + c * LD_C + 2 * r2);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(Ct + 2 * r2 + (long long)c * ld) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  asm volatile("bar.sync 1, %0;\n" ::"n"(32 * NW) : "memory");   // the C rows have landed for all working warps
+  const int r0 = warp * 16;
+  const bool act[2] = {true, true};
+  PTRACE_LAST(warp == 0, 1024 + 17 * 8);
+#pragma unroll 1
+  for (int cb = 0; cb < 16; cb++) {
+    const int c0 = 8 * cb;
+    PTRACE_LAST(warp == 0, 1024 + cb * 8 + 0);
+    if (cb > 0) {
+      const int b = cb & 1;
+      mbar_wait(&bars->fullR[b], ((cb - 1) >> 1) & 1);
+      // S = X[rows, 0:c0] * L[c0:c0+8, 0:c0]^T, two independent accumulation chains per m-tile
+      double s[2][2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) s[mt][ch][0] = s[mt][ch][1] = 0.0;
+      ll_accumulate<2>(s, Cs + t * LD_C + r0 + g, RB + b * TILE * LD_R + t * LD_R + g, cb, 8 * LD_C, 8 * LD_R, 4 * LD_C, 4 * LD_R, 8, act);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->emptyR[b]);   // this warp is done with the row-block buffer
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          double *p = Cs + (c0 + 2 * t + e) * LD_C + r0 + mt * 8 + g;
+          *p = (*p - s[mt][0][e]) - s[mt][1][e];
+        }
+      __syncwarp();
+    }
+    PTRACE_LAST(warp == 0, 1024 + cb * 8 + 3);
+    mbar_wait(&bars->fullD[cb], 0);
+    double dl[8][8], inv[8];
+    const double *D = Dbuf + cb * 64;   // D[c * 8 + r] = L[c0 + r][c0 + c]
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+#pragma unroll
+      for (int cp = 0; cp < 8; cp++) dl[c][cp] = cp < c ? D[cp * 8 + c] : 0.0;
+    const double my_inv = 1.0 / D[(lane & 7) * 9];   // one reciprocal per lane, handed round
+#pragma unroll
+    for (int c = 0; c < 8; c++) inv[c] = __shfl_sync(0xffffffffu, my_inv, c);
+    PTRACE_LAST(warp == 0, 1024 + cb * 8 + 1);
+    // substitution against the 8x8 diagonal block, one row per lane; finished columns go out at once, so nothing is left
+    // to write when the last block has been solved
+    if (lane < 16) {
+      double *px = Cs + c0 * LD_C + r0 + lane;
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) x[c] = px[c * LD_C];
+      solve_row8(x, dl, inv);
+      double *out = Ct + r0 + lane + (long long)c0 * ld;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        px[c * LD_C] = x[c];
+        out[(long long)c * ld] = x[c];
+      }
+    }
+    __syncwarp();
+    PTRACE_LAST(warp == 0, 1024 + cb * 8 + 2);
+  }
+  PTRACE_LAST(warp == 0, 1024 + 16 * 8);
+}
+
+constexpr int PANEL_FUSED_TILE_SMEM_BYTES = Follow<8>::SMEM_BYTES > POTRF_PW_SMEM_BYTES ? Follow<8>::SMEM_BYTES : POTRF_PW_SMEM_BYTES;
+
+// The same fused launch with one TRSM CTA per 128-row tile (eight working warps; only the C tile and a row block of L
+// are resident): covers up to 147 row tiles, at steps about 7 % slower than the 64-row form above.
+__global__ void __launch_bounds__(POTRF_PW_THREADS + 32, 1)
+panel_fused_tile_kernel(double *__restrict__ Lbase, long long ld, long long stride, long long diag_off, long long c_off,
+                        int tiles, int batch, int index_base, int n, int *info, int *flags) {
+  extern __shared__ __align__(16) double sm[];
+  if ((int)blockIdx.x < batch) {
+    __shared__ int s_pub;
+    const int m = blockIdx.x;
+    double *T = Lbase + (long long)m * stride + diag_off;
+    if (threadIdx.x == POTRF_PW_THREADS) s_pub = 0;
+    __syncthreads();
+    if (threadIdx.x >= POTRF_PW_THREADS) potrf_publisher(sm, T, ld, flags + 2 * m, &s_pub);
+    else potrf_pw_body<true>(sm, T, ld, index_base, n, info + m, &s_pub);
+    return;
+  }
+  constexpr int NW = 8, WORK = 32 * NW, ALL = WORK + 32;   // working threads, plus the loader warp
+  __shared__ __align__(8) FollowBars bars;
+  if (threadIdx.x >= ALL) return;
+  const int idx = (int)blockIdx.x - batch, m = idx / tiles, tile = idx - m * tiles;
+  double *base = Lbase + (long long)m * stride;
+  if (threadIdx.x >= WORK && threadIdx.x < WORK + 20) {
+    const int k = threadIdx.x - WORK;   // fullD[0..15], fullR[0..1]: 32 loader lanes each; emptyR[0..1]: one arrival per working warp
+    unsigned long long *bar = k < 16 ? &bars.fullD[k] : (k < 18 ? &bars.fullR[k - 16] : &bars.emptyR[k - 18]);
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(a), "r"(k < 18 ? 32 : NW) : "memory");
+  }
+  asm volatile("bar.sync 2, %0;\n" ::"n"(ALL) : "memory");
+  if (threadIdx.x >= WORK) {
+    trsm_tile_follow_loader(sm + Follow<NW>::C_DOUBLES, base + diag_off, ld, flags + 2 * m, &bars);
+    return;
+  }
+  trsm_tile_follow_compute<NW>(sm, base + c_off + (long long)tile * TILE, ld, &bars);
+  asm volatile("bar.sync 1, %0;\n" ::"n"(WORK) : "memory");
+  if (threadIdx.x == 0) {
+    if (atomicAdd(flags + 2 * m + 1, 1) == tiles - 1) {
+      flags[2 * m + 1] = 0;
+      *reinterpret_cast<volatile int *>(flags + 2 * m) = 0;
+    }
+  }
+}
+
 // W = L^-1 of one 128x128 lower-triangular tile per CTA (MODE-1 semantics of trsm_tile_kernel: W lower triangular,
 // strict upper zero; in place allowed).  X = L^-T is computed row block by row block -- its rows are independent, so
 // the eight warps never meet at a barrier -- left-looking over the column blocks at and right of the row block
@@ -990,6 +1190,7 @@ int panel_smem_setup(Handle *h) {
   GPB_CUDA(h, cudaFuncSetAttribute(trsm_ll_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmLL<2>::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(panel_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PanelFused<1>::SMEM_BYTES));
   GPB_CUDA(h, cudaFuncSetAttribute(panel_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PanelFused<2>::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(panel_fused_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_FUSED_TILE_SMEM_BYTES));
   return 0;
 }
 
@@ -1055,6 +1256,14 @@ int launch_potrf_trsm_at(Handle *h, double *L, long long ld, long long stride, l
   if (h->panel_fused && h->panel_impl == 0 && ntiles > 0 && batch <= PANEL_FUSED_MAX_BATCH) {
     if (h->trsm_mt_override == 1 && (long long)batch * (1 + 4 * ntiles) <= 148) mt = 1;
     else if ((long long)batch * (1 + 2 * ntiles) <= 148) mt = 2;
+  }
+  if (mt == 0 && h->panel_fused && h->panel_impl == 0 && ntiles > 0 && batch <= PANEL_FUSED_MAX_BATCH &&
+      (long long)batch * (1 + ntiles) <= 148) {
+    ProfScope ps__(h, PC_POTRF);
+    panel_fused_tile_kernel<<<batch * (1 + ntiles), POTRF_PW_THREADS + 32, PANEL_FUSED_TILE_SMEM_BYTES, h->stream>>>(
+        L, ld, stride, diag_off, c_off, ntiles, batch, index_base, n, info, h->panel_flags);
+    GPB_LAUNCH_CHECK(h);
+    return 0;
   }
   if (mt == 0) {
     int rc = launch_potrf_tile_at(h, L, ld, stride, diag_off, index_base, n, batch, info);
