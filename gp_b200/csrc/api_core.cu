@@ -82,6 +82,8 @@ extern "C" int gpb200_create(gpb200_handle_t *out, int device) {
   if (ds && ds[0] == '0') h->diag_split = 0;
   const char *tm = getenv("GPB200_TRSM_MT");
   if (tm && (tm[0] == '1' || tm[0] == '2')) h->trsm_mt_override = tm[0] - '0';
+  const char *fc = getenv("GPB200_FINE_CFG");
+  if (fc && fc[0] == '0') h->fine_cfg = 0;
   const char *pf = getenv("GPB200_PANEL_FUSED");
   if (pf && pf[0] == '0') h->panel_fused = 0;
   const char *ng = getenv("GPB200_NO_GRAPH");

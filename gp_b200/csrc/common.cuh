@@ -60,6 +60,7 @@ struct GemmParams {
   // derivative-observation trace epilogue (EPI_TRACE_DERIV): the matrix is nblocks x nblocks blocks of
   // n_grid x n_grid; block b carries derivative order order0 + b; theta is B x theta_stride
   int n_grid, order0, theta_stride;
+  int latency_hint;   // 1: this launch sits on a dependent chain (look-ahead Cholesky): small launches take the 16-warp fine tiles
 };
 
 struct Handle {
@@ -74,6 +75,7 @@ struct Handle {
   int trsm_pipelined = 1;     // 0: one tile per CTA (the first TRSM tile kernel); env GPB200_TRSM_PIPELINED
   int panel_impl = 0;         // 0: round-2 shared-memory panel kernels (POTRF with a panel warp); 1: the round-1 register-tile kernels; 2: round-2 POTRF without the panel warp (env GPB200_PANEL_V1 = 1 | 2)
   int trsm_mt_override = 0;   // tuning knob: 8-row mma tiles per warp of trsm_ll_kernel (1, 2, 4); env GPB200_TRSM_MT
+  int fine_cfg = 1;           // 64x64 CTAs of sixteen 16x16 warps for small chain launches (env GPB200_FINE_CFG)
   int panel_fused = 1;        // POTRF tile and the TRSM below it in one launch when one wave holds both (panel_fused_kernel); env GPB200_PANEL_FUSED
   int *panel_flags = nullptr; // 2 ints per matrix for panel_fused_kernel (visible column blocks, finished TRSM CTAs), zero between launches
   char err[512] = {0};

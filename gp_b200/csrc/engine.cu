@@ -225,6 +225,8 @@ static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int
   p.C0 = mref(Lbuf, np, stride);
   p.alpha = -1.0;
   p.beta = 1.0;
+  GemmParams pc = p;      // launches on the panel chain
+  pc.latency_hint = 1;
   cudaStream_t T = h->stream, P = h->pstream;
   struct Restore { Handle *h; cudaStream_t s; ~Restore() { h->stream = s; } } restore{h, T};
   size_t ev = 0;
@@ -238,8 +240,8 @@ static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int
     h->stream = P;
     for (int j = p0; j < p1; j++) {
       if (tl.count(j) > 0) {
-        p.tasks = tl.at(j);
-        if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, tl.count(j), batch))) return rc;
+        pc.tasks = tl.at(j);
+        if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, pc, tl.count(j), batch))) return rc;
       }
       if ((rc = launch_potrf_trsm(h, Lbuf, np, stride, j, nt - 1 - j, n, batch, info_dev))) return rc;
     }
@@ -247,8 +249,8 @@ static int chol_lookahead(Handle *h, double *Lbuf, int np, long long stride, int
     GPB_CUDA(h, cudaEventRecord(ev_panel, P));
     if (p1 < nt) {
       if (ev_trail) GPB_CUDA(h, cudaStreamWaitEvent(P, ev_trail, 0));
-      p.tasks = la1.at(panel);
-      if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, p, la1.count(panel), batch))) return rc;
+      pc.tasks = la1.at(panel);
+      if ((rc = launch_gemm(h, LAYOUT_NT, EPI_AXPBY, pc, la1.count(panel), batch))) return rc;
     }
     h->stream = T;
     GPB_CUDA(h, cudaStreamWaitEvent(T, ev_panel, 0));
@@ -303,6 +305,7 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
   TaskList ts, tw;
   rc = tasks_trtri(h, nt, &ts, &tw);
   if (rc) return rc;
+  const int chain = chol_uses_lookahead(h, nt, batch) ? 1 : 0;   // one or a few matrices: every launch is on the critical path
   for (int lvl = 0; lvl < ts.steps(); lvl++) {
     GemmParams p{};
     p.A = mref(Lbuf, np, stride);
@@ -310,6 +313,7 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
     p.C = mref(Sbuf, np, stride);
     p.alpha = 1.0;
     p.beta = 0.0;
+    p.latency_hint = chain;
     p.tasks = ts.at(lvl);
     rc = launch_gemm(h, LAYOUT_TT, EPI_AXPBY, p, ts.count(lvl), batch);
     if (rc) return rc;
@@ -319,6 +323,7 @@ int trtri_batched(Handle *h, double *Lbuf, double *Sbuf, int np, long long strid
     q.C = mref(Lbuf, np, stride);
     q.alpha = -1.0;
     q.beta = 0.0;
+    q.latency_hint = chain;
     q.tasks = tw.at(lvl);
     rc = launch_gemm(h, LAYOUT_TN, EPI_AXPBY, q, tw.count(lvl), batch);
     if (rc) return rc;

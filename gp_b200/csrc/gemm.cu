@@ -65,6 +65,10 @@ using CfgHalf8 = GemmCfg<4, 2, 64, 3, 2>;
 // operand tile is skipped for A as well as for B, and the redundant upper-right quadrant of a symmetric diagonal
 // tile is not computed at all (its CTA exits).
 using CfgQuarter = GemmCfg<2, 2, 64, 3, 3, 64>;
+// 4 Fine: the quarter tile on sixteen warps of 16x16 (one CTA per SM).  A 32x32 warp tile issues 64 DMMAs per 16-wide
+// k-chunk, about 1 050 cycles on its scheduler: a K = 128 update on the Cholesky's dependent chain is bound by that issue
+// rate, not by the SM's FP64 pipe.  Four times the warps, a quarter of the DMMAs each.  AXPBY epilogue, NT / TN / TT layouts (Cholesky chain, recursive inverse).
+using CfgFine = GemmCfg<4, 4, 64, 3, 1, 64>;
 constexpr int LD_KC = KC + 4;    // operand with k contiguous:             stage[128][20]
 constexpr int EPI_SCRATCH_DOUBLES = 4 * TILE + 5 * 16 + 8;
 static_assert(EPI_SCRATCH_DOUBLES * 8 <= CfgHalf8::SMEM_BYTES, "epilogue scratch must fit the pipeline buffers");
@@ -443,7 +447,12 @@ static int smem_setup_cfg(Handle *h) {
 int gemm_smem_setup(Handle *h) {
   int rc = smem_setup_cfg<CfgBig>(h);
   if (!rc) rc = smem_setup_cfg<CfgHalf8>(h);
-  return rc ? rc : smem_setup_cfg<CfgQuarter>(h);
+  if (!rc) rc = smem_setup_cfg<CfgQuarter>(h);
+  if (rc) return rc;
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<CfgFine, false, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgFine::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<CfgFine, true, true, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgFine::SMEM_BYTES));
+  GPB_CUDA(h, cudaFuncSetAttribute(gemm_tile_kernel<CfgFine, true, false, EPI_AXPBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgFine::SMEM_BYTES));
+  return 0;
 }
 
 template <class Cfg>
@@ -591,6 +600,12 @@ int launch_gemm(Handle *h, GemmLayout layout, GemmEpi epi, const GemmParams &p, 
     }
   }
   if (h->count_flops) h->executed_gemm_flops += executed_flops_host(h, p.tasks, ntasks, batch, c, c);
+  if (c == 3 && p.latency_hint && h->fine_cfg && epi == EPI_AXPBY && layout != LAYOUT_NN &&
+      (long long)ntasks * batch * CfgFine::NSPLIT <= 148) {
+    if (layout == LAYOUT_NT) return launch_one<CfgFine, false, false, EPI_AXPBY>(h, p, ntasks, batch);
+    if (layout == LAYOUT_TN) return launch_one<CfgFine, true, true, EPI_AXPBY>(h, p, ntasks, batch);
+    return launch_one<CfgFine, true, false, EPI_AXPBY>(h, p, ntasks, batch);
+  }
   if (c == 1) return launch_cfg<CfgBig>(h, layout, epi, p, ntasks, batch);
   if (c == 3) return launch_cfg<CfgQuarter>(h, layout, epi, p, ntasks, batch);
   return launch_cfg<CfgHalf8>(h, layout, epi, p, ntasks, batch);
