@@ -238,6 +238,7 @@ class BlockCyclicGP:
         self.info = be.info_scalar()
         self.panels = {}
         self.received = {}
+        self._square = None
         if self.native:
             return self._factor_native(dx, alpha, rho, sigma, jitter)
         for p in self.my_panels():
@@ -317,6 +318,10 @@ class BlockCyclicGP:
             self.panels[p] = P
         recv = [None, None]
         last_ticket = [None]
+        square = None
+        self._square = None
+        if self.keep_all:
+            square = be.empty(self.np_, self.np_)
         last_upd = {}          # my panel q -> event after the latest trailing update written into it (main stream)
         built = torch.cuda.Event()
         built.record(main)
@@ -386,7 +391,7 @@ class BlockCyclicGP:
                 nxt_buf, nxt_t = factor_and_bcast(nxt, cur_buf, cur_t)
             be.use_stream(main)
             mine = [q for q in self.my_panels() if q > nxt]
-            if mine:
+            if mine or square is not None:
                 for t in cur_t:
                     be.wait(t)
                 for q in mine:
@@ -395,6 +400,10 @@ class BlockCyclicGP:
                     ev = torch.cuda.Event()
                     ev.record(main)
                     last_upd[q] = ev
+                if square is not None:
+                    # the gradient wants the factor as one square: file the panel now, beside the chain, instead of in
+                    # 2 N^2 words of copies at the start of lml_grad
+                    be.panel_to_square(n, self.col0(p), self.ncols(p), cur_buf, self.ld(p), square)
             cur_buf, cur_t = nxt_buf, nxt_t
         done = torch.cuda.Event()
         done.record(ps)
@@ -404,6 +413,7 @@ class BlockCyclicGP:
         be.use_stream(main)
         if last_ticket[0] is not None:
             be.wait(last_ticket[0])
+        self._square = square
         info = self.info.clone()
         if self.world > 1:
             big = 1 << 30
@@ -423,10 +433,12 @@ class BlockCyclicGP:
         be, n, np_, pc = self.be, self.n, self.np_, self.pc
         torch = be.torch
         alpha, rho, sigma, _ = self.theta
-        Lsq = be.empty(np_, np_)
-        for p in range(self.npanels):
-            P = self.panels[p] if self.owner(p) == self.rank else self.received[p]
-            be.panel_to_square(n, self.col0(p), self.ncols(p), P, self.ld(p), Lsq)
+        Lsq = getattr(self, "_square", None)
+        if Lsq is None:   # host-driven schedule: assemble the square now
+            Lsq = be.empty(np_, np_)
+            for p in range(self.npanels):
+                P = self.panels[p] if self.owner(p) == self.rank else self.received[p]
+                be.panel_to_square(n, self.col0(p), self.ncols(p), P, self.ld(p), Lsq)
         nmine = be.my_columns(n, pc, self.rank, self.world)
         Xp = be.empty(np_, max(nmine, 1))
         S = be.empty(pc, max(nmine, 1))
@@ -438,7 +450,8 @@ class BlockCyclicGP:
         part = be.vector(8 * np_, zero=False)
         be.inverse_rows(n, pc, self.rank, self.world, Lsq, Xp, S, Wd)
         be.solve_partials(n, pc, self.rank, self.world, Lsq, Xp, ypad, z_mine, a, sums2, part)
-        del S, Wd, Lsq
+        del S, Wd
+        Lsq = None
         qf = sums2[0:1].clone()
         if self.world > 1:
             be.allreduce(a)
