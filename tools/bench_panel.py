@@ -14,9 +14,11 @@ def run_variant():
     label_skip_inverse = os.environ.get("GPB200_TRSM_MT") is not None
     h = capi.Handle(0)
     out = {}
-    for what, name in ((0, "potrf_tile"), (1, "trsm_tiles"), (2, "tile_inverse")):
-        for nt, batch in ((32, 1), (8, 1), (32, 2), (32, 4), (8, 32), (32, 128)):
+    for what, name in ((0, "potrf_tile"), (1, "trsm_tiles"), (2, "tile_inverse"), (3, "potrf+trsm")):
+        for nt, batch in ((32, 1), (8, 1), (32, 2), (32, 4), (8, 32), (32, 128), (64, 1), (128, 1)):
             if what == 0 and nt != 32:
+                continue
+            if what != 3 and nt > 32:
                 continue
             if what == 2 and label_skip_inverse:
                 continue
@@ -29,7 +31,7 @@ if __name__ == "__main__":
         run_variant()
         sys.exit(0)
     res = {}
-    for label, env in (("round2_panel_warp", {}), ("round1_v1", {"GPB200_PANEL_V1": "1"}),
+    for label, env in (("round2_panel_warp", {}), ("round2_two_launches", {"GPB200_PANEL_FUSED": "0"}), ("round1_v1", {"GPB200_PANEL_V1": "1"}),
                        ("ll_mt1", {"GPB200_TRSM_MT": "1"}), ("ll_mt2", {"GPB200_TRSM_MT": "2"})):
         e = dict(os.environ); e.update(env)
         r = subprocess.run([sys.executable, __file__, "child"], env=e, capture_output=True, text=True)
