@@ -461,7 +461,7 @@ def main():
         for rec in latency.values():
             rec.pop("_check")
         line["latency"] = dict(latency, what="device-resident LML+gradient latency per call, B = 1 and B = 4 (CUDA-graph replay, "
-                                             "look-ahead Cholesky, quarter-tile GEMM CTAs), CUDA events, rank 0")
+                                             "look-ahead Cholesky with fused POTRF+TRSM launches, quarter- and fine-tile GEMM CTAs), CUDA events, rank 0")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_evals = 8
