@@ -104,15 +104,18 @@ extern "C" int gpb200_mg_comm_destroy(gpb200_handle_t h) {
 
 // Broadcast of `count` doubles from `root`, enqueued on the handle's communication stream behind everything
 // enqueued so far on the compute stream (the root's data is final, a receiver's buffer is no longer read).
-// Returns a ticket; gpb200_mg_wait makes the compute stream wait for that collective.  With one rank: a no-op.
+// Returns a ticket; gpb200_mg_wait makes the compute stream wait for that collective.  With one rank there is no
+// collective and the ticket stands for the point the compute stream had reached.
 extern "C" int gpb200_mg_bcast(gpb200_handle_t h, double *buf, long long count, int root, long long *ticket) {
   CHECK_H(h);
   if (!h->cstream) BAD_ARG(h, 1, "mg_bcast: gpb200_mg_comm_init first");
   const long long t = h->mg_tickets++;
   if (ticket) *ticket = t;
-  if (h->mg_world == 1) return 0;
   cudaEvent_t e = h->mg_events[(size_t)(t % MG_EVENT_RING)];
   GPB_CUDA(h, cudaEventRecord(e, h->stream));
+  // one rank: no collective, but the ticket still orders "data final on the stream that produced it" before a wait on
+  // another stream (callers run the panel chain and the trailing updates on different streams)
+  if (h->mg_world == 1) return 0;
   GPB_CUDA(h, cudaStreamWaitEvent(h->cstream, e, 0));
   GPB_NCCL(h, g_nccl.Broadcast(buf, buf, (size_t)count, NCCL_DOUBLE, root, h->nccl_comm, h->cstream));
   GPB_CUDA(h, cudaEventRecord(e, h->cstream));
@@ -121,7 +124,6 @@ extern "C" int gpb200_mg_bcast(gpb200_handle_t h, double *buf, long long count, 
 
 extern "C" int gpb200_mg_wait(gpb200_handle_t h, long long ticket) {
   CHECK_H(h);
-  if (h->mg_world == 1) return 0;
   if (ticket < 0 || ticket >= h->mg_tickets || h->mg_tickets - ticket > MG_EVENT_RING)
     BAD_ARG(h, 2, "mg_wait: unknown or expired ticket");
   GPB_CUDA(h, cudaStreamWaitEvent(h->stream, h->mg_events[(size_t)(ticket % MG_EVENT_RING)], 0));
