@@ -427,6 +427,9 @@ trsm_tiles_pipelined_kernel(const double *Ldiag_base, double *Cbase, long long l
 // trsm_ll_kernel        the rows of X = C L^-T are independent: each warp runs its rows through all sixteen steps with
 //                       no block barrier; a CTA takes 32 or 64 rows so that ONE matrix spreads a block column over the GPU
 // tile_inverse_ll_kernel  X = L^-T row block by row block into the unused upper triangle of the staged tile
+// panel_fused_kernel<MT>, panel_fused_tile_kernel   POTRF and TRSM of a block column in ONE launch: the TRSM CTAs follow
+//                       the diagonal CTA's factorisation block by block through flags in global memory (64-row CTAs with
+//                       the staged L resident, or 128-row CTAs with a double-buffered row block of L)
 // Per-phase cycle counts (tools/panel_trace.py, instrumented build) are in profiles/panel_trace_r02.txt.
 // ------------------------------------------------------------------------------------------------
 constexpr int LD_T = TILE + 4;  // column-major tile in shared memory, 132: conflict-free mma fragment reads

@@ -79,7 +79,8 @@ GPB200_API double gpb200_executed_gemm_flops(gpb200_handle_t h);
 
 /* tuning aid (not a reference interface): times one panel kernel in isolation on `batch` synthetic
  * matrices of nt x nt 128-tiles.  what: 0 POTRF of a diagonal tile, 1 TRSM of the nt-1 tiles below it,
- * 2 inverse of the nt diagonal tiles.  ms_out[0] = mean device time per launch (CUDA events). */
+ * 2 inverse of the nt diagonal tiles, 3 POTRF + TRSM of the first block column the way the Cholesky issues them (one fused
+ * launch on the latency path, else two).  ms_out[0] = mean device time per launch (CUDA events). */
 GPB200_API int gpb200_debug_bench_panel(gpb200_handle_t h, int what, int nt, int batch, int reps, double *ms_out);
 /* instrumented builds only (-DGPB_PANEL_TRACE): 2048 clock64 stamps left by CTA 0 of the panel kernels; -1 otherwise */
 GPB200_API int gpb200_debug_panel_trace(gpb200_handle_t h, long long *out2048);
