@@ -199,11 +199,12 @@ bool chol_uses_lookahead(const Handle *h, int nt, int batch) {
   return h->lookahead && h->pstream && batch <= h->lookahead_max_batch && (long long)batch * nt <= 256 && nt >= 3;
 }
 // panel width of the look-ahead schedule in tiles: one tile column per chain step for small matrices (the chain is all
-// there is); from nt = 24 on two, which halves the number of bulk launches and doubles their K (measured at N = 4096,
-// B = 1: 3.39 -> 3.35 ms; N = 2048: 0.94 -> 0.97 ms)
+// there is); wider panels halve the number of bulk launches and double their K as the matrix grows.  Measured, B = 1,
+// LML + gradient: N = 2048 0.94 ms with 1 / 0.97 with 2; N = 4096 3.39 / 3.34 / 3.45 ms with 1 / 2 / 4; N = 8192 19.5 /
+// 19.2 / 19.8 ms with 2 / 4 / 8; N = 16 384 135.1 / 132.1 / 132.5; N = 32 768 1040 / 1018 / 1008.
 int chol_lookahead_panel(const Handle *h, int nt) {
   if (h->chol_panel_override > 0) return std::min(nt, h->chol_panel_override);
-  return nt >= 24 ? 2 : 1;
+  return nt >= 192 ? 8 : (nt >= 48 ? 4 : (nt >= 24 ? 2 : 1));
 }
 
 // Look-ahead schedule (small batches; one matrix does not fill the GPU and the panel chain of one POTRF tile and
